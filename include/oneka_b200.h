@@ -1,0 +1,164 @@
+/*
+ * oneka_b200.h -- C ABI of the B200-native capture-zone hot path (liboneka_b200.so).
+ *
+ * The reference (RandalJBarnes/OnekaPy) is pure Python and has no FFI layer; its boundary
+ * for this path is the Python function API.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference tree).  A maintainer binds these
+ * with ctypes; onekapy_b200/_cabi.py is that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - every function returns ONEKA_OK (0) or a negative error code and never throws;
+ *     oneka_last_error() gives the message for the calling thread's last failure;
+ *   - pointers named *_dev are DEVICE pointers (caller-owned, e.g. torch tensors' data_ptr());
+ *     pointers named *_host are host pointers; the *_host entry points do their own copies;
+ *   - one oneka_ctx per GPU; work is enqueued on the context's stream (oneka_set_stream) and
+ *     is asynchronous unless stated otherwise; a context is not thread-safe;
+ *   - there is no CPU fallback: oneka_create() fails when no sm_100 CUDA device is usable.
+ *
+ * Array layouts (row-major, C order)
+ *   well_xy[nw][2]      well coordinates x, y                       (oneka/model.py:158-171)
+ *   q[R][nw]            well discharges per realization             (oneka/stochastic.py:224-228)
+ *   cond[R] poro[R] thick[R]  conductivity, porosity, thickness     (oneka/stochastic.py:231-233)
+ *   coef[R][6]          regional coefficients A..F                  (oneka/stochastic.py:241)
+ *   start_xy[P][2]      start ring around the target well           (oneka/capturezone.py:113-115)
+ *   counts[nrows][ncols] uint32, row = y index, col = x index       (oneka/probabilityfield.py:148; pgrid with weight 1)
+ */
+#ifndef ONEKA_B200_H
+#define ONEKA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONEKA_ABI_VERSION 1
+
+/* return codes */
+#define ONEKA_OK            0
+#define ONEKA_ERR_ARG      -1
+#define ONEKA_ERR_CUDA     -2
+#define ONEKA_ERR_NOMEM    -3
+#define ONEKA_ERR_NODEVICE -4
+
+/* per-path status words (status[R][P]) */
+#define ONEKA_PATH_OK          0
+#define ONEKA_PATH_AQUIFER_DRY 1   /* AquiferError inside feval: oneka/model.py:343-344, 380-381; trace truncated as by capturezone.py:249-253 */
+#define ONEKA_PATH_MAX_ATTEMPT 2   /* guard the reference lacks (capturezone.py:221 has no iteration cap) */
+#define ONEKA_PATH_NONFINITE   3   /* guard the reference lacks (it would spin forever on nan) */
+#define ONEKA_PATH_TRACE_FULL  4   /* oneka_trace only: max_verts reached */
+
+typedef struct oneka_ctx oneka_ctx;
+
+/* The aquifer model that is constant over a run: oneka/model.py:131-196 (Model attributes)
+ * plus the solver settings of oneka/capturezone.py:127 (compute_backtrace arguments). */
+typedef struct {
+    int32_t nw;            /* number of wells                                                  */
+    int32_t confined;      /* 1: compute_velocity_confined (model.py:392-427); 0: compute_velocity (model.py:353-389) */
+    double  base;          /* aquifer base elevation (model.py:179); does not enter the velocity */
+    double  xo, yo;        /* origin of the regional quadratic = target well (stochastic.py:239 -> model.py:490-491) */
+    double  duration;      /* capturezone.py:127; negative = forward tracking                  */
+    double  tol;           /* absolute local error bound [m]                                   */
+    double  maxstep;       /* space-step cap [m]                                               */
+    int64_t max_attempts;  /* per-path cap on DOPRI attempts; <= 0 selects the default (1<<22)   */
+} oneka_model_desc;
+
+/* A fixed node-centred lattice: node (i, j) sits at (xmin + j*deltax, ymin + i*deltay)
+ * exactly as oneka/probabilityfield.py:306-307 computes cx, cy. */
+typedef struct {
+    double  xmin, ymin;
+    double  deltax, deltay;
+    int32_t nrows, ncols;
+    double  umbra;         /* vector-to-raster range, probabilityfield.py:264 (insert) */
+} oneka_lattice;
+
+/* Run statistics, filled by oneka_read_stats (which synchronises the stream). */
+typedef struct {
+    uint64_t attempts;         /* DOPRI5 attempts summed over all particles ("particle-steps") */
+    uint64_t steps;            /* accepted steps (= segments rasterised)                       */
+    uint64_t paths;            /* particles tracked                                            */
+    uint64_t n_not_ok;         /* paths whose status != ONEKA_PATH_OK                          */
+    uint64_t n_clipped;        /* segments whose raster window was clipped by the lattice edge */
+    uint64_t exact_tests;      /* cells whose FP32 classification fell inside the error band and were re-tested in exact FP64 */
+    double   bbox[4];          /* min x, max x, min y, max y over every vertex (incl. start points) */
+} oneka_stats;
+
+const char *oneka_last_error(void);
+int         oneka_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+oneka_ctx *oneka_create(int device);                    /* NULL on failure; see oneka_last_error */
+void       oneka_destroy(oneka_ctx *ctx);
+int        oneka_set_stream(oneka_ctx *ctx, void *cuda_stream);         /* cudaStream_t; NULL = legacy default */
+int        oneka_set_workspace_limit(oneka_ctx *ctx, uint64_t bytes);   /* cap for the per-realization registration bitmaps */
+int        oneka_synchronize(oneka_ctx *ctx);
+uint64_t   oneka_launch_count(const oneka_ctx *ctx);    /* kernels launched by this context so far */
+/* When enabled, CUDA events bracket every launch of the tracking/raster kernel and of the flush
+ * kernel on the context's stream; oneka_kernel_ms returns the accumulated device time. */
+int        oneka_set_profiling(oneka_ctx *ctx, int enabled);
+int        oneka_kernel_ms(oneka_ctx *ctx, double *track_ms, double *flush_ms, uint64_t *track_launches, int reset);
+
+/* ---- Model evaluation at points ----------------------------------------------------- *
+ * Replaces Model.compute_potential / compute_discharge / compute_velocity_confined /
+ * compute_head / compute_velocity (oneka/model.py:207-427) for npts points of ONE model.
+ * out_host[npts][8] = potential, Qx, Qy, Vx_confined, Vy_confined, head, Vx, Vy
+ * (head, Vx, Vy are nan where the reference raises AquiferError).  Synchronous.          */
+int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_host,
+                           const double *q_host, double cond, double poro, double thick,
+                           const double *coef_host, int64_t npts, const double *pts_host, double *out_host);
+
+/* ---- Backtraces with stored vertices (test hook for the tracking kernel alone) -------- *
+ * Replaces compute_backtrace (oneka/capturezone.py:127-253) for R x P particles.
+ * verts_dev[R][P][max_verts][2]; nverts_dev[R][P] counts vertices incl. the start point. */
+int oneka_trace(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_dev,
+                int64_t R, int32_t P,
+                const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                const double *coef_dev, const double *start_xy_dev,
+                int32_t max_verts, double *verts_dev, int32_t *nverts_dev, uint8_t *status_dev, int32_t *attempts_dev);
+
+/* ---- Rasterise given traces (test hook for the rasteriser alone) ---------------------- *
+ * Replaces ProbabilityField.insert per segment + register(1.0) per realization
+ * (oneka/probabilityfield.py:264-310, 342-359) on a FIXED lattice:
+ * trace t = verts_dev[offsets[t] .. offsets[t+1]) belongs to realization real_of_dev[t]
+ * (0 <= real_of < nreal); counts_dev[nrows][ncols] += 1 per realization that marks the cell. */
+int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntraces,
+                        const int64_t *offsets_dev, const double *verts_dev, const int32_t *real_of_dev,
+                        int64_t nreal, uint32_t *counts_dev);
+
+/* ---- The hot path: track + rasterise + register, R realizations x P paths ------------- *
+ * Replaces the body of the realization loop, i.e. R calls of compute_capturezone
+ * (oneka/capturezone.py:51-123, called at oneka/stochastic.py:264-265 and
+ * oneka/deterministic.py:232-233) with weight 1.0 on a fixed lattice.
+ * counts_dev is accumulated (+=).  lat == NULL or counts_dev == NULL: tracking only
+ * (bounding box / end points / statistics; no rasterisation).
+ * Optional per-path outputs may be NULL: end_xy_dev[R][P][2], nverts_dev[R][P], status_dev[R][P]. */
+int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                  const double *well_xy_dev, int64_t R, int32_t P,
+                  const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                  const double *coef_dev, const double *start_xy_dev,
+                  uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev);
+
+/* Statistics of everything enqueued since the last oneka_reset_stats.  Synchronises. */
+int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out);
+int oneka_reset_stats(oneka_ctx *ctx);
+
+/* Same as oneka_capture with HOST buffers: copies the parameter rows to the device, runs,
+ * and copies counts (nrows*ncols uint32, overwritten) back.  Synchronous.
+ * This is the call the reference-facing Python layer makes for one batch (bench `e2e`). */
+int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                       const double *well_xy_host, int64_t R, int32_t P,
+                       const double *q_host, const double *cond_host, const double *poro_host, const double *thick_host,
+                       const double *coef_host, const double *start_xy_host,
+                       uint32_t *counts_host, double *end_xy_host, int32_t *nverts_host, uint8_t *status_host,
+                       oneka_stats *stats_out);
+
+/* ---- FP64 pipe probe ------------------------------------------------------------------ *
+ * Times a register-resident DFMA kernel (no memory traffic) and reports the achieved
+ * FP64 rate; bench.py uses it as the measured FP64 roofline denominator.  Synchronous.  */
+int oneka_fp64_probe(oneka_ctx *ctx, int iters, double *tflops_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEKA_B200_H */

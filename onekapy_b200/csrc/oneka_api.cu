@@ -1,0 +1,715 @@
+// oneka_api.cu -- kernels + C ABI of liboneka_b200.so (see include/oneka_b200.h).
+//
+// Build (done by __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC \
+//        -Iinclude onekapy_b200/csrc/oneka_api.cu -o onekapy_b200/liboneka_b200.so
+#include "oneka_device.cuh"
+#include "../../include/oneka_b200.h"
+
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <new>
+
+using namespace oneka;
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(ONEKA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int TRACK_THREADS = 128;          // 4 warps per CTA; every warp stays inside one realization
+constexpr int N_STATS = 16;
+
+struct oneka_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    unsigned int *bitmaps = nullptr;        // registration bitmaps, all-zero between calls
+    size_t bitmap_bytes = 0;
+    size_t workspace_limit = (size_t)16 << 30;
+    unsigned long long *stats_dev = nullptr;
+    uint64_t launches = 0;
+    // host-buffer staging (oneka_capture_host), grow-only
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    // profiling
+    bool profiling = false;
+    struct EvPair { cudaEvent_t a, b; int kind; };
+    std::vector<EvPair> events;
+    double track_ms = 0.0, flush_ms = 0.0;
+    uint64_t track_launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------
+template <bool CONFINED>
+__device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc,
+                                                  double2 *s_wxy, double *s_w)
+{
+    const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
+    const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
+    for (int i = threadIdx.x; i < tp.nw; i += blockDim.x) {
+        s_wxy[i] = make_double2(tp.well_xy[2 * i], tp.well_xy[2 * i + 1]);
+        s_w[i] = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;     // q/(2 pi) [/(H n)]
+    }
+    if (threadIdx.x == 0) {
+        const double *cf = tp.coef + 6 * r;
+        rc.a2 = 2.0 * cf[0] * scale;
+        rc.b2 = 2.0 * cf[1] * scale;
+        rc.c = cf[2] * scale;
+        rc.d = cf[3] * scale;
+        rc.e = cf[4] * scale;
+        rc.A = cf[0]; rc.B = cf[1]; rc.F = cf[5];
+        rc.k = k; rc.H = H; rc.n = n;
+        rc.half_kH2 = 0.5 * k * (H * H);
+        rc.xo = tp.xo; rc.yo = tp.yo;
+    }
+    __syncthreads();
+}
+
+// One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
+template <bool CONFINED, int MODE>
+__global__ void __launch_bounds__(TRACK_THREADS)
+track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
+{
+    extern __shared__ double2 s_dyn[];
+    __shared__ RealConsts rc;
+    double2 *s_wxy = s_dyn;
+    double *s_w = reinterpret_cast<double *>(s_dyn + tp.nw);
+
+    const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
+    const long long r = blockIdx.x / chunks;
+    const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
+    stage_realization<CONFINED>(tp, r, rc, s_wxy, s_w);
+    unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
+    dopri_track<CONFINED, MODE>(tp, L, bm, rc, s_wxy, s_w, r, p, p < tp.P);
+}
+
+// register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per
+// bitmap word position, looping over its slice of realization slots; per-bit counters live
+// in registers, bitmap words are zeroed as they are consumed, counts get one RED per nonzero
+// counter.  Reads are coalesced (consecutive threads = consecutive words of one slot).
+__global__ void __launch_bounds__(256)
+flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, LatticeDev L, unsigned int *counts)
+{
+    const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.words) return;
+    const long long s0 = (long long)blockIdx.y * slots_per_y;
+    const long long s1 = min(nslots, s0 + slots_per_y);
+    unsigned int cnt[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) cnt[b] = 0;
+    bool any = false;
+    for (long long s = s0; s < s1; ++s) {
+        unsigned int *pw = bitmaps + (size_t)s * L.words + w;
+        const unsigned int v = *pw;
+        if (v) {
+            *pw = 0u;
+            any = true;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) cnt[b] += (v >> b) & 1u;
+        }
+    }
+    if (!any) return;
+    const int i = (int)(w / L.wpr);
+    const int j0 = (int)(w % L.wpr) * 32;
+    unsigned int *row = counts + (size_t)i * L.ncols + j0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+        if (cnt[b]) atomicAdd(row + b, cnt[b]);
+}
+
+// test hook: one thread per given trace, same raster_seg as the fused kernel
+__global__ void __launch_bounds__(128)
+raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, const double *verts,
+                     const int *real_of, long long s0, long long s1, unsigned int *bitmaps, unsigned long long *stats)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntraces) return;
+    const long long r = real_of[t];
+    if (r < s0 || r >= s1) return;
+    unsigned int *bm = bitmaps + (size_t)(r - s0) * L.words;
+    RasterCounters ctr = {0u, 0u};
+    unsigned long long nseg = 0;
+    for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
+        raster_seg(L, bm, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
+        ++nseg;
+    }
+    atomicAdd(stats + STAT_STEPS, nseg);
+    if (ctr.clipped) atomicAdd(stats + STAT_CLIPPED, (unsigned long long)ctr.clipped);
+    if (ctr.exact) atomicAdd(stats + STAT_EXACT, (unsigned long long)ctr.exact);
+}
+
+// Model.compute_* at points (model.py:207-427); one CTA, wells staged twice (both scalings)
+__global__ void __launch_bounds__(128)
+eval_points_kernel(TrackParams tp, long long npts, const double *pts, double *out)
+{
+    extern __shared__ double2 s_dyn[];
+    __shared__ RealConsts rc_c, rc_u;
+    double2 *s_wxy = s_dyn;
+    double *s_wc = reinterpret_cast<double *>(s_dyn + tp.nw);
+    double *s_wu = s_wc + tp.nw;
+    stage_realization<true>(tp, 0, rc_c, s_wxy, s_wc);
+    stage_realization<false>(tp, 0, rc_u, s_wxy, s_wu);
+    for (long long i = threadIdx.x; i < npts; i += blockDim.x) {
+        const double x = pts[2 * i], y = pts[2 * i + 1];
+        double *o = out + 8 * i;
+        // potential, model.py:226-237 + 259-266
+        const double dx0 = x - rc_u.xo, dy0 = y - rc_u.yo;
+        double pot = rc_u.A * dx0 * dx0 + rc_u.B * dy0 * dy0 + rc_u.c * dx0 * dy0 + rc_u.d * dx0 + rc_u.e * dy0 + rc_u.F;
+        double qx = -(rc_u.a2 * dx0 + rc_u.c * dy0 + rc_u.d);           // model.py:303-304
+        double qy = -(rc_u.b2 * dy0 + rc_u.c * dx0 + rc_u.e);
+        for (int w = 0; w < tp.nw; ++w) {
+            const double dx = x - s_wxy[w].x, dy = y - s_wxy[w].y;
+            const double r2 = dx * dx + dy * dy;
+            pot += 0.5 * s_wu[w] * log(r2);
+            qx -= s_wu[w] * dx / r2;                                     // model.py:312-313
+            qy -= s_wu[w] * dy / r2;
+        }
+        o[0] = pot; o[1] = qx; o[2] = qy;
+        double fx, fy;
+        field_feval<true>(rc_c, s_wxy, s_wc, tp.nw, x, y, fx, fy);
+        o[3] = -fx; o[4] = -fy;
+        o[5] = o[6] = o[7] = nan("");
+        if (pot > 0.0) {
+            o[5] = (pot < rc_u.half_kH2) ? sqrt(2.0 * pot / rc_u.k) : (pot + rc_u.half_kH2) / (rc_u.k * rc_u.H);   // model.py:345-349
+            if (field_feval<false>(rc_u, s_wxy, s_wu, tp.nw, x, y, fx, fy) == PATH_OK) { o[6] = -fx; o[7] = -fy; }
+        }
+    }
+}
+
+// FP64 pipe probe: 8 independent DFMA chains per thread, registers only.
+__global__ void __launch_bounds__(256)
+fp64_probe_kernel(int iters, double seed, double *sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) sink[0] = s;     // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------
+// Host helpers
+// ------------------------------------------------------------------------------------------
+static int check_model(const oneka_model_desc *m)
+{
+    if (!m) return fail(ONEKA_ERR_ARG, "model descriptor is NULL");
+    if (m->nw < 0) return fail(ONEKA_ERR_ARG, "nw must be >= 0");
+    if (!(m->tol > 0.0)) return fail(ONEKA_ERR_ARG, "tol must be > 0 (capturezone.py:139-142)");
+    if (!(m->maxstep > 0.0)) return fail(ONEKA_ERR_ARG, "maxstep must be > 0 (capturezone.py:144-146)");
+    if (!(m->duration == m->duration)) return fail(ONEKA_ERR_ARG, "duration is nan");
+    return ONEKA_OK;
+}
+
+static int make_lattice(const oneka_lattice *lat, LatticeDev &L)
+{
+    if (!(lat->deltax > 0.0) || !(lat->deltay > 0.0))
+        return fail(ONEKA_ERR_ARG, "<deltax>, <deltay> must be > 0 (probabilityfield.py:127-131)");
+    if (lat->nrows <= 0 || lat->ncols <= 0) return fail(ONEKA_ERR_ARG, "lattice must have nrows, ncols > 0");
+    if (!(lat->umbra >= 0.0)) return fail(ONEKA_ERR_ARG, "umbra must be >= 0");
+    L.xmin = lat->xmin; L.ymin = lat->ymin; L.dx = lat->deltax; L.dy = lat->deltay;
+    L.nrows = lat->nrows; L.ncols = lat->ncols; L.wpr = (lat->ncols + 31) / 32;
+    L.umbra = lat->umbra;
+    L.umbra2 = lat->umbra * lat->umbra;
+    L.dx32 = (float)lat->deltax; L.dy32 = (float)lat->deltay; L.umbra2_32 = (float)L.umbra2;
+    L.maxd = lat->deltax > lat->deltay ? lat->deltax : lat->deltay;
+    L.words = (unsigned long long)L.nrows * (unsigned long long)L.wpr;
+    return ONEKA_OK;
+}
+
+static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_dev, long long R, int P,
+                              const double *q, const double *cond, const double *poro, const double *thick,
+                              const double *coef, const double *start, unsigned long long *stats)
+{
+    TrackParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.nw = m->nw; tp.P = P; tp.R = R;
+    tp.duration = m->duration; tp.tol = m->tol; tp.maxstep = m->maxstep;
+    long long ma = m->max_attempts > 0 ? m->max_attempts : ((long long)1 << 22);
+    tp.max_attempts = (int)(ma > 0x7fffffffLL ? 0x7fffffffLL : ma);
+    tp.xo = m->xo; tp.yo = m->yo;
+    tp.well_xy = well_xy_dev;
+    tp.q = q; tp.cond = cond; tp.poro = poro; tp.thick = thick; tp.coef = coef; tp.start_xy = start;
+    tp.stats = stats;
+    return tp;
+}
+
+static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double)); }
+
+static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->bitmap_bytes) return ONEKA_OK;
+    if (ctx->bitmaps) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFree(ctx->bitmaps)); ctx->bitmaps = nullptr; ctx->bitmap_bytes = 0; }
+    cudaError_t e = cudaMalloc(&ctx->bitmaps, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ONEKA_ERR_NOMEM, "cudaMalloc(%zu) for registration bitmaps failed: %s", bytes, cudaGetErrorString(e)); }
+    ctx->bitmap_bytes = bytes;
+    CUDA_TRY(cudaMemsetAsync(ctx->bitmaps, 0, bytes, ctx->stream));
+    return ONEKA_OK;
+}
+
+static void prof_begin(oneka_ctx *ctx, int kind)
+{
+    if (!ctx->profiling) return;
+    oneka_ctx::EvPair ev;
+    cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.kind = kind;
+    cudaEventRecord(ev.a, ctx->stream);
+    ctx->events.push_back(ev);
+}
+static void prof_end(oneka_ctx *ctx)
+{
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->events.back().b, ctx->stream);
+}
+
+template <int MODE>
+static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps)
+{
+    const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
+    const long long nblk = tp.R * chunks;
+    if (nblk <= 0) return ONEKA_OK;
+    if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
+    const size_t smem = track_smem(tp.nw);
+    if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
+    prof_begin(ctx, 0);
+    if (m->confined) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps);
+    } else {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<false, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps);
+    }
+    prof_end(ctx);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ONEKA_OK;
+}
+
+static int launch_flush(oneka_ctx *ctx, const LatticeDev &L, long long nslots, unsigned int *counts)
+{
+    const unsigned gx = (unsigned)((L.words + 255) / 256);
+    // aim for >= 2 waves of 148 SMs x 8 CTAs
+    long long want_y = (2LL * ctx->sm_count * 8 + gx - 1) / gx;
+    if (want_y < 1) want_y = 1;
+    if (want_y > nslots) want_y = nslots;
+    if (want_y > 65535) want_y = 65535;
+    const long long per_y = (nslots + want_y - 1) / want_y;
+    const unsigned gy = (unsigned)((nslots + per_y - 1) / per_y);
+    prof_begin(ctx, 1);
+    flush_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(ctx->bitmaps, nslots, per_y, L, counts);
+    prof_end(ctx);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ONEKA_OK;
+}
+
+static long long slots_for(const oneka_ctx *ctx, const LatticeDev &L, long long want)
+{
+    const size_t per = (size_t)L.words * sizeof(unsigned int);
+    long long cap = (long long)(ctx->workspace_limit / per);
+    return want < cap ? want : cap;
+}
+
+static int reset_stats_async(oneka_ctx *ctx)
+{
+    unsigned long long init[N_STATS];
+    memset(init, 0, sizeof(init));
+    init[STAT_XMIN] = ~0ULL; init[STAT_YMIN] = ~0ULL;    // atomicMin targets
+    init[STAT_XMAX] = 0ULL; init[STAT_YMAX] = 0ULL;      // atomicMax targets
+    // tiny pageable copy; cudaMemcpyAsync from a stack buffer is staged by the driver before return
+    CUDA_TRY(cudaMemcpyAsync(ctx->stats_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    return ONEKA_OK;
+}
+
+static double undkey(unsigned long long k)
+{
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *oneka_last_error(void) { return g_err; }
+int oneka_abi_version(void) { return ONEKA_ABI_VERSION; }
+
+oneka_ctx *oneka_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fail(ONEKA_ERR_NODEVICE, "no CUDA device: %s (this library has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { fail(ONEKA_ERR_ARG, "device %d out of range [0,%d)", device, n); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail(ONEKA_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major != 10) {
+        fail(ONEKA_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(ONEKA_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    oneka_ctx *ctx = new (std::nothrow) oneka_ctx();
+    if (!ctx) { fail(ONEKA_ERR_NOMEM, "out of host memory"); return nullptr; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc(&ctx->stats_dev, N_STATS * sizeof(unsigned long long)) != cudaSuccess) {
+        fail(ONEKA_ERR_NOMEM, "cudaMalloc(stats) failed"); delete ctx; return nullptr;
+    }
+    if (reset_stats_async(ctx) != ONEKA_OK) { cudaFree(ctx->stats_dev); delete ctx; return nullptr; }
+    cudaStreamSynchronize(ctx->stream);
+    g_err[0] = 0;
+    return ctx;
+}
+
+void oneka_destroy(oneka_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    if (ctx->bitmaps) cudaFree(ctx->bitmaps);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->stats_dev) cudaFree(ctx->stats_dev);
+    delete ctx;
+}
+
+int oneka_set_stream(oneka_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return ONEKA_OK;
+}
+
+int oneka_set_workspace_limit(oneka_ctx *ctx, uint64_t bytes)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    ctx->workspace_limit = (size_t)bytes;
+    return ONEKA_OK;
+}
+
+int oneka_synchronize(oneka_ctx *ctx)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ONEKA_OK;
+}
+
+uint64_t oneka_launch_count(const oneka_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int oneka_set_profiling(oneka_ctx *ctx, int enabled)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    ctx->profiling = enabled != 0;
+    return ONEKA_OK;
+}
+
+int oneka_kernel_ms(oneka_ctx *ctx, double *track_ms, double *flush_ms, uint64_t *track_launches, int reset)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto &ev : ctx->events) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        if (ev.kind == 0) { ctx->track_ms += ms; ctx->track_launches++; }
+        else ctx->flush_ms += ms;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    ctx->events.clear();
+    if (track_ms) *track_ms = ctx->track_ms;
+    if (flush_ms) *flush_ms = ctx->flush_ms;
+    if (track_launches) *track_launches = ctx->track_launches;
+    if (reset) { ctx->track_ms = ctx->flush_ms = 0.0; ctx->track_launches = 0; }
+    return ONEKA_OK;
+}
+
+int oneka_reset_stats(oneka_ctx *ctx)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return reset_stats_async(ctx);
+}
+
+int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out)
+{
+    if (!ctx || !out) return fail(ONEKA_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    unsigned long long h[N_STATS];
+    CUDA_TRY(cudaMemcpyAsync(h, ctx->stats_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out->attempts = h[STAT_ATTEMPTS]; out->steps = h[STAT_STEPS]; out->paths = h[STAT_PATHS];
+    out->n_not_ok = h[STAT_NOT_OK]; out->n_clipped = h[STAT_CLIPPED]; out->exact_tests = h[STAT_EXACT];
+    if (h[STAT_PATHS] == 0) {
+        out->bbox[0] = out->bbox[2] = INFINITY; out->bbox[1] = out->bbox[3] = -INFINITY;
+    } else {
+        out->bbox[0] = undkey(h[STAT_XMIN]); out->bbox[1] = undkey(h[STAT_XMAX]);
+        out->bbox[2] = undkey(h[STAT_YMIN]); out->bbox[3] = undkey(h[STAT_YMAX]);
+    }
+    return ONEKA_OK;
+}
+
+int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_host,
+                           const double *q_host, double cond, double poro, double thick,
+                           const double *coef_host, int64_t npts, const double *pts_host, double *out_host)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (!m || m->nw < 0 || npts < 0 || !coef_host || (npts && (!pts_host || !out_host)) || (m->nw && (!well_xy_host || !q_host)))
+        return fail(ONEKA_ERR_ARG, "bad argument to oneka_eval_points_host");
+    if (npts == 0) return ONEKA_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int nw = m->nw;
+    const size_t nd = (size_t)3 * nw + 3 + 6 + 2 * (size_t)npts + 8 * (size_t)npts;
+    double *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, nd * sizeof(double)));
+    double *d_wxy = buf, *d_q = d_wxy + 2 * nw, *d_k = d_q + nw, *d_n = d_k + 1, *d_H = d_n + 1, *d_cf = d_H + 1;
+    double *d_pts = d_cf + 6, *d_out = d_pts + 2 * npts;
+    cudaStream_t s = ctx->stream;
+    int rc = ONEKA_OK;
+    do {
+#define TRY2(expr) if ((expr) != cudaSuccess) { rc = fail(ONEKA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); break; }
+        if (nw) { TRY2(cudaMemcpyAsync(d_wxy, well_xy_host, 2 * nw * sizeof(double), cudaMemcpyHostToDevice, s));
+                  TRY2(cudaMemcpyAsync(d_q, q_host, nw * sizeof(double), cudaMemcpyHostToDevice, s)); }
+        const double sc[3] = {cond, poro, thick};
+        TRY2(cudaMemcpyAsync(d_k, sc, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+        TRY2(cudaMemcpyAsync(d_cf, coef_host, 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+        TRY2(cudaMemcpyAsync(d_pts, pts_host, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, s));
+        oneka_model_desc mm = *m;
+        if (!(mm.tol > 0)) mm.tol = 1.0;
+        if (!(mm.maxstep > 0)) mm.maxstep = 1.0;
+        TrackParams tp = make_track(&mm, d_wxy, 1, 1, d_q, d_k, d_n, d_H, d_cf, nullptr, ctx->stats_dev);
+        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * sizeof(double));
+        if (smem > 48 * 1024) TRY2(cudaFuncSetAttribute(eval_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_points_kernel<<<1, 128, smem, s>>>(tp, npts, d_pts, d_out);
+        ctx->launches++;
+        TRY2(cudaGetLastError());
+        TRY2(cudaMemcpyAsync(out_host, d_out, 8 * npts * sizeof(double), cudaMemcpyDeviceToHost, s));
+        TRY2(cudaStreamSynchronize(s));
+#undef TRY2
+    } while (0);
+    cudaFree(buf);
+    return rc;
+}
+
+int oneka_trace(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_dev,
+                int64_t R, int32_t P,
+                const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                const double *coef_dev, const double *start_xy_dev,
+                int32_t max_verts, double *verts_dev, int32_t *nverts_dev, uint8_t *status_dev, int32_t *attempts_dev)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (R < 0 || P <= 0 || max_verts < 1 || !verts_dev) return fail(ONEKA_ERR_ARG, "bad R/P/max_verts/verts");
+    if (R == 0) return ONEKA_OK;
+    if (!cond_dev || !poro_dev || !thick_dev || !coef_dev || !start_xy_dev || (m->nw && (!q_dev || !well_xy_dev)))
+        return fail(ONEKA_ERR_ARG, "NULL parameter array");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    TrackParams tp = make_track(m, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev, ctx->stats_dev);
+    tp.verts = verts_dev; tp.max_verts = max_verts;
+    tp.nverts = nverts_dev; tp.status = status_dev; tp.attempts = attempts_dev;
+    LatticeDev L;
+    memset(&L, 0, sizeof(L));
+    return launch_track<2>(ctx, m, tp, L, nullptr);
+}
+
+int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntraces,
+                        const int64_t *offsets_dev, const double *verts_dev, const int32_t *real_of_dev,
+                        int64_t nreal, uint32_t *counts_dev)
+{
+    if (!ctx || !lat) return fail(ONEKA_ERR_ARG, "NULL argument");
+    if (ntraces < 0 || nreal < 0) return fail(ONEKA_ERR_ARG, "negative count");
+    LatticeDev L;
+    int rc = make_lattice(lat, L);
+    if (rc) return rc;
+    if (ntraces == 0 || nreal == 0) return ONEKA_OK;
+    if (!offsets_dev || !verts_dev || !real_of_dev || !counts_dev) return fail(ONEKA_ERR_ARG, "NULL array");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const long long slots = slots_for(ctx, L, nreal);
+    if (slots < 1) return fail(ONEKA_ERR_NOMEM, "workspace limit %zu B is smaller than one registration bitmap (%llu B)",
+                               ctx->workspace_limit, (unsigned long long)(L.words * 4));
+    rc = ensure_bitmaps(ctx, (size_t)slots * L.words * sizeof(unsigned int));
+    if (rc) return rc;
+    for (long long s0 = 0; s0 < nreal; s0 += slots) {
+        const long long s1 = (s0 + slots < nreal) ? s0 + slots : nreal;
+        raster_traces_kernel<<<(unsigned)((ntraces + 127) / 128), 128, 0, ctx->stream>>>(
+            L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        rc = launch_flush(ctx, L, s1 - s0, counts_dev);
+        if (rc) return rc;
+    }
+    return ONEKA_OK;
+}
+
+int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                  const double *well_xy_dev, int64_t R, int32_t P,
+                  const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                  const double *coef_dev, const double *start_xy_dev,
+                  uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (R < 0 || P <= 0) return fail(ONEKA_ERR_ARG, "R must be >= 0 and P > 0 (capturezone.py:68-70)");
+    if (R == 0) return ONEKA_OK;
+    if (!cond_dev || !poro_dev || !thick_dev || !coef_dev || !start_xy_dev || (m->nw && (!q_dev || !well_xy_dev)))
+        return fail(ONEKA_ERR_ARG, "NULL parameter array");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const bool raster = lat != nullptr && counts_dev != nullptr;
+    LatticeDev L;
+    memset(&L, 0, sizeof(L));
+    long long slots = R;
+    if (raster) {
+        rc = make_lattice(lat, L);
+        if (rc) return rc;
+        slots = slots_for(ctx, L, R);
+        if (slots < 1) return fail(ONEKA_ERR_NOMEM, "workspace limit %zu B is smaller than one registration bitmap (%llu B)",
+                                   ctx->workspace_limit, (unsigned long long)(L.words * 4));
+        rc = ensure_bitmaps(ctx, (size_t)slots * L.words * sizeof(unsigned int));
+        if (rc) return rc;
+    }
+    // keep each launch below 2^31 CTAs
+    const int chunks = (P + TRACK_THREADS - 1) / TRACK_THREADS;
+    const long long max_r = 0x7fffffffLL / chunks;
+    if (slots > max_r) slots = max_r;
+    for (long long r0 = 0; r0 < R; r0 += slots) {
+        const long long nr = (r0 + slots < R) ? slots : R - r0;
+        TrackParams tp = make_track(m, well_xy_dev, nr, P, q_dev + (size_t)r0 * m->nw, cond_dev + r0, poro_dev + r0,
+                                    thick_dev + r0, coef_dev + 6 * r0, start_xy_dev, ctx->stats_dev);
+        tp.end_xy = end_xy_dev ? end_xy_dev + 2 * (size_t)r0 * P : nullptr;
+        tp.nverts = nverts_dev ? nverts_dev + (size_t)r0 * P : nullptr;
+        tp.status = status_dev ? status_dev + (size_t)r0 * P : nullptr;
+        if (raster) {
+            rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps);
+            if (rc) return rc;
+            rc = launch_flush(ctx, L, nr, counts_dev);
+            if (rc) return rc;
+        } else {
+            rc = launch_track<0>(ctx, m, tp, L, nullptr);
+            if (rc) return rc;
+        }
+    }
+    return ONEKA_OK;
+}
+
+int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                       const double *well_xy_host, int64_t R, int32_t P,
+                       const double *q_host, const double *cond_host, const double *poro_host, const double *thick_host,
+                       const double *coef_host, const double *start_xy_host,
+                       uint32_t *counts_host, double *end_xy_host, int32_t *nverts_host, uint8_t *status_host,
+                       oneka_stats *stats_out)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (R < 0 || P <= 0) return fail(ONEKA_ERR_ARG, "R must be >= 0 and P > 0");
+    if (!cond_host || !poro_host || !thick_host || !coef_host || !start_xy_host || (m->nw && (!q_host || !well_xy_host)))
+        return fail(ONEKA_ERR_ARG, "NULL parameter array");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const bool raster = lat != nullptr && counts_host != nullptr;
+    const size_t nw = (size_t)m->nw, RP = (size_t)R * P;
+    const size_t ncell = raster ? (size_t)lat->nrows * lat->ncols : 0;
+    // carve one staging allocation (8-byte aligned pieces first)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_wxy = carve(2 * nw * 8), o_q = carve((size_t)R * nw * 8), o_k = carve(R * 8), o_n = carve(R * 8), o_H = carve(R * 8);
+    const size_t o_cf = carve((size_t)R * 6 * 8), o_st = carve((size_t)P * 2 * 8);
+    const size_t o_end = carve(end_xy_host ? RP * 16 : 0), o_nv = carve(nverts_host ? RP * 4 : 0), o_stt = carve(status_host ? RP : 0);
+    const size_t o_cnt = carve(ncell * 4);
+    if (off > ctx->stage_bytes) {
+        if (ctx->stage) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFree(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->stage, off);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ONEKA_ERR_NOMEM, "cudaMalloc(%zu) for staging failed", off); }
+        ctx->stage_bytes = off;
+    }
+    char *base = (char *)ctx->stage;
+    cudaStream_t s = ctx->stream;
+    if (nw) {
+        CUDA_TRY(cudaMemcpyAsync(base + o_wxy, well_xy_host, 2 * nw * 8, cudaMemcpyHostToDevice, s));
+        if (R) CUDA_TRY(cudaMemcpyAsync(base + o_q, q_host, (size_t)R * nw * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (R) {
+        CUDA_TRY(cudaMemcpyAsync(base + o_k, cond_host, R * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(base + o_n, poro_host, R * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(base + o_H, thick_host, R * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(base + o_cf, coef_host, (size_t)R * 48, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(base + o_st, start_xy_host, (size_t)P * 16, cudaMemcpyHostToDevice, s));
+    if (raster) CUDA_TRY(cudaMemsetAsync(base + o_cnt, 0, ncell * 4, s));
+    if (stats_out) { rc = reset_stats_async(ctx); if (rc) return rc; }
+    rc = oneka_capture(ctx, m, raster ? lat : nullptr, (const double *)(base + o_wxy), R, P,
+                       (const double *)(base + o_q), (const double *)(base + o_k), (const double *)(base + o_n),
+                       (const double *)(base + o_H), (const double *)(base + o_cf), (const double *)(base + o_st),
+                       raster ? (uint32_t *)(base + o_cnt) : nullptr,
+                       end_xy_host ? (double *)(base + o_end) : nullptr,
+                       nverts_host ? (int32_t *)(base + o_nv) : nullptr,
+                       status_host ? (uint8_t *)(base + o_stt) : nullptr);
+    if (rc) return rc;
+    if (raster) CUDA_TRY(cudaMemcpyAsync(counts_host, base + o_cnt, ncell * 4, cudaMemcpyDeviceToHost, s));
+    if (end_xy_host && RP) CUDA_TRY(cudaMemcpyAsync(end_xy_host, base + o_end, RP * 16, cudaMemcpyDeviceToHost, s));
+    if (nverts_host && RP) CUDA_TRY(cudaMemcpyAsync(nverts_host, base + o_nv, RP * 4, cudaMemcpyDeviceToHost, s));
+    if (status_host && RP) CUDA_TRY(cudaMemcpyAsync(status_host, base + o_stt, RP, cudaMemcpyDeviceToHost, s));
+    if (stats_out) return oneka_read_stats(ctx, stats_out);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ONEKA_OK;
+}
+
+int oneka_fp64_probe(oneka_ctx *ctx, int iters, double *tflops_out, double *ms_out)
+{
+    if (!ctx || iters <= 0) return fail(ONEKA_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    fp64_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(iters / 8 + 1, 1.0, sink);     // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(a, ctx->stream));
+        fp64_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, 1.0, sink);
+        CUDA_TRY(cudaEventRecord(b, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    CUDA_TRY(cudaGetLastError());
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return ONEKA_OK;
+}
+
+}  // extern "C"

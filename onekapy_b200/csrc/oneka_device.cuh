@@ -1,0 +1,405 @@
+// oneka_device.cuh -- device functions of the capture-zone hot path (sm_100a).
+//
+// Three pieces, each written B200-first (FP64 CUDA-core pipe for the integrator, FP32 pipe +
+// L2 atomics for the rasteriser; nothing here is a contraction, so no tensor cores):
+//
+//   field_*      analytic velocity field          reference: oneka/model.py:269-315, 318-427
+//   dopri_track  Dormand-Prince 5(4) backtrace    reference: oneka/capturezone.py:199-247
+//   raster_seg   segment -> registration bitmap   reference: oneka/probabilityfield.py:296-310, 407-427
+//
+// Results policy: the tracker reproduces the reference's step sequence (same accept/reject
+// tests, same controller, same operation order where it decides anything) with rounding-level
+// differences only (FMA contraction, Newton reciprocal) -- endpoints agree to ~1e-12 relative,
+// far inside the 1e-6 bar.  The rasteriser is BIT-EXACT: cells are classified in FP32 with a
+// rigorous error band and every cell inside the band is re-tested with the reference's own
+// unfused IEEE-double formula (__dmul_rn/__dadd_rn/__ddiv_rn are never contracted).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+namespace oneka {
+
+// ------------------------------------------------------------------------------------------
+// Status words (mirror include/oneka_b200.h)
+enum : int { PATH_OK = 0, PATH_AQUIFER_DRY = 1, PATH_MAX_ATTEMPT = 2, PATH_NONFINITE = 3, PATH_TRACE_FULL = 4 };
+
+// Per-realization constants staged in shared memory by each CTA.
+struct RealConsts {
+    // regional gradient terms; confined: pre-divided by thickness*porosity
+    double a2, b2, c, d, e;          // 2A, 2B, C, D, E  (x 1/(H n) when confined)
+    // unconfined only
+    double A, B, F;                  // potential terms (model.py:226-231)
+    double k, H, n;                  // conductivity, thickness, porosity
+    double half_kH2;                 // 0.5*k*H^2 (model.py:345)
+    double xo, yo;
+};
+
+struct TrackParams {
+    int nw;
+    int P;
+    long long R;                     // realizations in this launch
+    double duration, tol, maxstep;
+    int max_attempts;
+    double xo, yo;
+    const double *well_xy;           // [nw][2]
+    const double *q, *cond, *poro, *thick, *coef;   // per-realization rows (already offset to this launch)
+    const double *start_xy;          // [P][2]
+    // optional outputs (already offset)
+    double *end_xy; int *nverts; unsigned char *status; int *attempts;
+    // oneka_trace only
+    double *verts; int max_verts;
+    // statistics
+    unsigned long long *stats;       // see STAT_* below
+};
+
+enum : int { STAT_ATTEMPTS = 0, STAT_STEPS = 1, STAT_PATHS = 2, STAT_NOT_OK = 3, STAT_CLIPPED = 4, STAT_EXACT = 5,
+             STAT_XMIN = 6, STAT_XMAX = 7, STAT_YMIN = 8, STAT_YMAX = 9, STAT_WORDS = 10 };
+
+struct LatticeDev {
+    double xmin, ymin, dx, dy;
+    int nrows, ncols, wpr;           // wpr = 32-bit words per bitmap row
+    double umbra, umbra2;            // umbra2 = umbra*umbra rounded once (probabilityfield.py:296)
+    float dx32, dy32, umbra2_32;
+    double maxd;                     // max(dx, dy)
+    unsigned long long words;        // words per bitmap = nrows*wpr
+};
+
+// ------------------------------------------------------------------------------------------
+// 1/a for a in the normal range: MUFU.RCP64H seed + one cubic Newton step (3 DFMA).
+// Relative error ~1 ulp; replaces the ~20-instruction IEEE divide in the well loop.
+__device__ __forceinline__ double rcp_fast(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// seed-and-correction split: returns y0 and t such that 1/a = y0 + y0*t
+__device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
+{
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    double e = fma(-a, y0, 1.0);
+    t = fma(e, e, e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Backtracking velocity  f(x,y) = -V(x,y).
+//
+// confined   (stochastic.py:254-256 -> model.py:423-427 -> 300-315):
+//     -V = [ (2A dx + C dy + D) + sum_w q_w/(2 pi) (x-x_w)/r_w^2 ] / (H n)
+//   with every constant pre-divided by H*n when the CTA stages its realization, so one well
+//   costs 10 FP64-pipe instructions (2 DADD, DMUL, 5 DFMA, 2 DMUL... see DESIGN.md) + 1 MUFU.
+// unconfined (stochastic.py:258-260 -> model.py:377-389, 341-350, 226-237, 259-266):
+//   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
+//   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
+//   reference's AquiferError -> PATH_AQUIFER_DRY.
+template <bool CONFINED>
+__device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *__restrict__ s_wxy,
+                                           const double *__restrict__ s_w, int nw,
+                                           double x, double y, double &fx, double &fy)
+{
+    const double dx0 = x - rc.xo;
+    const double dy0 = y - rc.yo;
+    double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
+    double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
+    double lsum = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < nw; ++i) {
+        const double2 wxy = s_wxy[i];
+        const double w = s_w[i];
+        const double dx = x - wxy.x;
+        const double dy = y - wxy.y;
+        const double r2 = fma(dy, dy, dx * dx);
+        double y0, t;
+        rcp_parts(r2, y0, t);
+        const double s0 = w * y0;
+        const double s = fma(s0, t, s0);
+        gx = fma(s, dx, gx);
+        gy = fma(s, dy, gy);
+        if (!CONFINED) lsum = fma(w, log(r2), lsum);
+    }
+    if (CONFINED) {
+        fx = gx;
+        fy = gy;
+        return PATH_OK;
+    } else {
+        // potential (model.py:226-237); 0.5*lsum = sum q ln(r2)/(4 pi) since w = q/(2 pi)
+        double pot = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
+        pot = fma(0.5, lsum, pot);
+        if (!(pot > 0.0)) return PATH_AQUIFER_DRY;                      // model.py:343-344 (nan also ends the trace)
+        double head;
+        if (pot < rc.half_kH2) head = sqrt(2.0 * pot / rc.k);           // model.py:345-346
+        else head = (pot + rc.half_kH2) / (rc.k * rc.H);                // model.py:347-349
+        if (!(head > 0.0)) return PATH_AQUIFER_DRY;                     // model.py:380-381
+        const double sat = (head > rc.H) ? rc.H : head;                 // model.py:382-387
+        const double inv = 1.0 / (sat * rc.n);
+        fx = gx * inv;
+        fy = gy * inv;
+        return PATH_OK;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Rasteriser.
+//
+// insert() (probabilityfield.py:296-310) marks every lattice node of the clipped window whose
+// distancesquared() (:407-427) to the segment is < umbra^2.  Here:
+//   1. the window is computed with the reference's own IEEE operations (sub, sub, div, floor);
+//   2. each node is classified in FP32 relative to endpoint a (projection clamp form, 9 FP32
+//      ops on the otherwise idle FP32 pipe).  |d2_fp32 - d2_exact| <= 44 eps32 L^2 where
+//      L = max(|bax|,|bay|) + umbra + max(dx,dy) bounds every |cax|,|cay| in the window
+//      (derivation in DESIGN.md); the reference's own FP64 value is within 32 eps64 (..)^2 of
+//      exact, which is 2^-29 times smaller.  With band E = 128 eps32 L^2:
+//         d2_fp32 <  umbra^2 - E  -> inside  (same answer as the reference)
+//         d2_fp32 >  umbra^2 + E  -> outside (same answer as the reference)
+//         otherwise (incl. nan)   -> evaluate the reference formula in unfused FP64;
+//   3. the bits of one bitmap word are OR-ed into the realization's bitmap with one RED.OR.
+// Segments shorter than 1e-10 m (never produced by the integrator except by an exact clamp)
+// take the exact path for every node; zero-length segments set nothing (0/0 = nan in :421).
+
+__device__ __forceinline__ double exact_distancesquared(double ax, double ay, double bx, double by, double cx, double cy)
+{
+    // probabilityfield.py:407-427, operation for operation, never contracted
+    const double bax = __dsub_rn(bx, ax);
+    const double bay = __dsub_rn(by, ay);
+    const double cax = __dsub_rn(cx, ax);
+    const double cay = __dsub_rn(cy, ay);
+    const double perpdot = __dsub_rn(__dmul_rn(bax, cay), __dmul_rn(bay, cax));
+    const double dot = __dadd_rn(__dmul_rn(bax, cax), __dmul_rn(bay, cay));
+    const double length2 = __dadd_rn(__dmul_rn(bax, bax), __dmul_rn(bay, bay));
+    const double alpha2 = __ddiv_rn(__dmul_rn(perpdot, perpdot), length2);
+    const double beta2 = __ddiv_rn(__dmul_rn(dot, dot), length2);
+    double d2;
+    if (dot < 0)
+        d2 = __dadd_rn(alpha2, beta2);
+    else if (beta2 > length2)
+        d2 = __dadd_rn(__dsub_rn(__dadd_rn(alpha2, beta2), __dmul_rn(2.0, dot)), length2);
+    else
+        d2 = alpha2;
+    return d2;
+}
+
+struct RasterCounters { unsigned int clipped, exact; };
+
+__device__ __noinline__ bool exact_cell_test(const LatticeDev &L, double ax, double ay, double bx, double by, int i, int j)
+{
+    const double cx = __dadd_rn(L.xmin, __dmul_rn((double)j, L.dx));     // probabilityfield.py:306
+    const double cy = __dadd_rn(L.ymin, __dmul_rn((double)i, L.dy));     // probabilityfield.py:307
+    return exact_distancesquared(ax, ay, bx, by, cx, cy) < L.umbra2;     // :309 (nan -> false)
+}
+
+__device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__restrict__ bm,
+                                           double ax, double ay, double bx, double by, RasterCounters &ctr)
+{
+    // ---- window, probabilityfield.py:298-301 ----
+    const double mnx = (bx < ax) ? bx : ax, mxx = (bx > ax) ? bx : ax;
+    const double mny = (by < ay) ? by : ay, mxy = (by > ay) ? by : ay;
+    const double fl = floor(__ddiv_rn(__dsub_rn(__dsub_rn(mnx, L.umbra), L.xmin), L.dx));
+    const double fr = floor(__ddiv_rn(__dsub_rn(__dadd_rn(mxx, L.umbra), L.xmin), L.dx));
+    const double fb = floor(__ddiv_rn(__dsub_rn(__dsub_rn(mny, L.umbra), L.ymin), L.dy));
+    const double ft = floor(__ddiv_rn(__dsub_rn(__dadd_rn(mxy, L.umbra), L.ymin), L.dy));
+    const double lo_x = fmax(fl, 0.0), hi_x = fmin(fr + 1.0, (double)L.ncols);
+    const double lo_y = fmax(fb, 0.0), hi_y = fmin(ft + 1.0, (double)L.nrows);
+    if (fl < 0.0 || fb < 0.0 || fr + 1.0 > (double)L.ncols || ft + 1.0 > (double)L.nrows) ctr.clipped++;
+    if (!(lo_x < hi_x) || !(lo_y < hi_y)) return;                        // empty window (also nan)
+    const int left = (int)lo_x, right = (int)hi_x, bottom = (int)lo_y, top = (int)hi_y;
+
+    const double bax = __dsub_rn(bx, ax), bay = __dsub_rn(by, ay);
+    const double len2 = __dadd_rn(__dmul_rn(bax, bax), __dmul_rn(bay, bay));
+    if (!(len2 > 0.0)) return;                                           // 0/0 -> nan -> no node is marked
+    const bool all_exact = len2 < 1e-20;
+
+    // ---- FP32 set-up, relative to endpoint a ----
+    const float fbax = (float)bax, fbay = (float)bay;
+    const float finv = 1.0f / fmaf(fbay, fbay, fbax * fbax);
+    const float base_x = (float)(fma((double)left, L.dx, L.xmin) - ax);
+    const float base_y = (float)(fma((double)bottom, L.dy, L.ymin) - ay);
+    const double Lm = fmax(fabs(bax), fabs(bay)) + L.umbra + L.maxd;
+    const float E = (float)(128.0 * 1.1920928955078125e-07 * Lm * Lm);
+    const float thr_in = L.umbra2_32 - E, thr_out = L.umbra2_32 + E;
+
+    const int w0 = left >> 5, w1 = (right - 1) >> 5;
+    for (int i = bottom; i < top; ++i) {
+        const float cay = fmaf((float)(i - bottom), L.dy32, base_y);
+        unsigned int *row = bm + (size_t)i * L.wpr;
+        for (int w = w0; w <= w1; ++w) {
+            const int j0 = max(left, w << 5), j1 = min(right, (w << 5) + 32);
+            unsigned int mask = 0;
+            for (int j = j0; j < j1; ++j) {
+                const float cax = fmaf((float)(j - left), L.dx32, base_x);
+                const float dot = fmaf(fbax, cax, fbay * cay);
+                const float t = __saturatef(dot * finv);
+                const float px = fmaf(-t, fbax, cax);
+                const float py = fmaf(-t, fbay, cay);
+                const float d2 = fmaf(px, px, py * py);
+                bool in = d2 < thr_in;
+                if (all_exact || !(in || d2 > thr_out)) {
+                    ctr.exact++;
+                    in = exact_cell_test(L, ax, ay, bx, by, i, j);
+                }
+                mask |= (in ? 1u : 0u) << (j & 31);
+            }
+            if (mask) atomicOr(row + w, mask);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sortable encoding of doubles for atomicMin/atomicMax on unsigned 64-bit
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
+//   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
+template <bool CONFINED, int MODE>
+__device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, unsigned int *bm,
+                                            const RealConsts &rc, const double2 *s_wxy, const double *s_w,
+                                            long long r, int p, bool active)
+{
+    // Dormand-Prince tableau, capturezone.py:202-209
+    constexpr double a20 = 1.0 / 5.0;
+    constexpr double a30 = 3.0 / 40.0, a31 = 9.0 / 40.0;
+    constexpr double a40 = 44.0 / 45.0, a41 = -56.0 / 15.0, a42 = 32.0 / 9.0;
+    constexpr double a50 = 19372.0 / 6561.0, a51 = -25360.0 / 2187.0, a52 = 64448.0 / 6561.0, a53 = -212.0 / 729.0;
+    constexpr double a60 = 9017.0 / 3168.0, a61 = -355.0 / 33.0, a62 = 46732.0 / 5247.0, a63 = 49.0 / 176.0, a64 = -5103.0 / 18656.0;
+    constexpr double a70 = 35.0 / 384.0, a72 = 500.0 / 1113.0, a73 = 125.0 / 192.0, a74 = -2187.0 / 6784.0, a75 = 11.0 / 84.0;
+    constexpr double e0 = 71.0 / 57600.0, e1 = -1.0 / 40.0, e2 = -71.0 / 16695.0, e3 = 71.0 / 1920.0, e4 = -17253.0 / 339200.0, e5 = 22.0 / 525.0;
+    constexpr double EPS = DBL_EPSILON;                                   // :200
+
+    const int nw = tp.nw;
+    const double duration = tp.duration, tol = tp.tol, maxstep = tp.maxstep;
+    const double adur = fabs(duration);
+
+    double x = 0.0, y = 0.0;
+    double t = 0.0;                                                        // :212
+    double dt = 0.1 * ((duration > 0.0) ? 1.0 : ((duration < 0.0) ? -1.0 : 0.0));   // :213
+    int status = PATH_OK;
+    int nattempt = 0, nvert = 0;
+    double bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+    RasterCounters ctr = {0u, 0u};
+    double *vout = nullptr;
+
+    double k1x = 0.0, k1y = 0.0;
+    bool running = active;
+    if (active) {
+        x = tp.start_xy[2 * p];
+        y = tp.start_xy[2 * p + 1];
+        nvert = 1;                                                         // :215 the start point is the first vertex
+        bx0 = bx1 = x; by0 = by1 = y;
+        if (MODE == 2) {
+            vout = tp.verts + ((size_t)r * tp.P + p) * (size_t)tp.max_verts * 2;
+            if (tp.max_verts > 0) { vout[0] = x; vout[1] = y; }
+        }
+        status = field_feval<CONFINED>(rc, s_wxy, s_w, nw, x, y, k1x, k1y);   // :219
+        if (status != PATH_OK) running = false;
+    }
+
+    while (running && fabs(t) < adur) {                                    // :221
+        if (nattempt >= tp.max_attempts) { status = PATH_MAX_ATTEMPT; break; }
+        ++nattempt;
+        if (fabs(t + dt) > adur) dt = duration - t;                        // :223-224
+
+        double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
+        int st;
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);              // :227
+        if (!CONFINED && st) { status = st; break; }
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                                   fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                          // :228
+        if (!CONFINED && st) { status = st; break; }
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                                   fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                           // :229
+        if (!CONFINED && st) { status = st; break; }
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                                   fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
+                                   fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);            // :230
+        if (!CONFINED && st) { status = st; break; }
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                                   fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
+                                   fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
+        if (!CONFINED && st) { status = st; break; }
+
+        const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);                 // :233
+        const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
+        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, xt, yt, k7x, k7y);                                                    // :236
+        if (!CONFINED && st) { status = st; break; }
+
+        const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));               // :237-238
+        const double ey = dt * fma(e5, k6y, fma(e4, k5y, fma(e3, k4y, fma(e2, k3y, fma(e1, k7y, e0 * k1y)))));
+        const double est = fmax(fabs(ex), fabs(ey));
+        const double ddx = xt - x, ddy = yt - y;
+        const double ds = sqrt(fma(ddy, ddy, ddx * ddx));                                                                    // :239
+
+        if (!(isfinite(est) && isfinite(ds))) { status = PATH_NONFINITE; break; }   // the reference would loop forever on nan
+
+        if (est < tol && ds < maxstep) {                                   // :241-245
+            t = t + dt;
+            k1x = k7x; k1y = k7y;
+            if (MODE == 1) raster_seg(L, bm, x, y, xt, yt, ctr);
+            x = xt; y = yt;
+            bx0 = fmin(bx0, x); bx1 = fmax(bx1, x); by0 = fmin(by0, y); by1 = fmax(by1, y);
+            if (MODE == 2) {
+                if (nvert < tp.max_verts) { vout[2 * nvert] = x; vout[2 * nvert + 1] = y; }
+                else status = PATH_TRACE_FULL;
+            }
+            ++nvert;
+        }
+
+        // :247  dt = 0.9 * min((tol/(est+EPS))**(1/5), maxstep/(ds+EPS), 10) * dt
+        // x**0.2 < c  <=>  x < c^5 : the pow is evaluated only when the error term governs.
+        const double cb = fmin(maxstep * rcp_fast(ds + EPS), 10.0);
+        const double xr = tol * rcp_fast(est + EPS);
+        const double c2 = cb * cb;
+        double mn = cb;
+        if (xr < c2 * c2 * cb) mn = fmin(pow(xr, 0.2), cb);
+        dt = 0.9 * mn * dt;
+    }
+
+    // ---- per-path outputs ----
+    if (active) {
+        const size_t g = (size_t)r * tp.P + p;
+        if (tp.end_xy) { tp.end_xy[2 * g] = x; tp.end_xy[2 * g + 1] = y; }
+        if (tp.nverts) tp.nverts[g] = nvert;
+        if (tp.status) tp.status[g] = (unsigned char)status;
+        if (tp.attempts) tp.attempts[g] = nattempt;
+    }
+
+    // ---- statistics: warp-reduce, one atomic per warp per word ----
+    unsigned long long att = (unsigned long long)nattempt, stp = active ? (unsigned long long)(nvert - 1) : 0ull;
+    unsigned int npath = active ? 1u : 0u, nbad = (active && status != PATH_OK) ? 1u : 0u;
+    unsigned int ncl = ctr.clipped, nex = ctr.exact;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        att += __shfl_down_sync(0xffffffffu, att, o);
+        stp += __shfl_down_sync(0xffffffffu, stp, o);
+        npath += __shfl_down_sync(0xffffffffu, npath, o);
+        nbad += __shfl_down_sync(0xffffffffu, nbad, o);
+        ncl += __shfl_down_sync(0xffffffffu, ncl, o);
+        nex += __shfl_down_sync(0xffffffffu, nex, o);
+        bx0 = fmin(bx0, __shfl_down_sync(0xffffffffu, bx0, o));
+        bx1 = fmax(bx1, __shfl_down_sync(0xffffffffu, bx1, o));
+        by0 = fmin(by0, __shfl_down_sync(0xffffffffu, by0, o));
+        by1 = fmax(by1, __shfl_down_sync(0xffffffffu, by1, o));
+    }
+    if ((threadIdx.x & 31) == 0 && npath) {
+        atomicAdd(tp.stats + STAT_ATTEMPTS, att);
+        atomicAdd(tp.stats + STAT_STEPS, stp);
+        atomicAdd(tp.stats + STAT_PATHS, (unsigned long long)npath);
+        if (nbad) atomicAdd(tp.stats + STAT_NOT_OK, (unsigned long long)nbad);
+        if (ncl) atomicAdd(tp.stats + STAT_CLIPPED, (unsigned long long)ncl);
+        if (nex) atomicAdd(tp.stats + STAT_EXACT, (unsigned long long)nex);
+        atomicMin(tp.stats + STAT_XMIN, dkey(bx0));
+        atomicMax(tp.stats + STAT_XMAX, dkey(bx1));
+        atomicMin(tp.stats + STAT_YMIN, dkey(by0));
+        atomicMax(tp.stats + STAT_YMAX, dkey(by1));
+    }
+}
+
+}  // namespace oneka

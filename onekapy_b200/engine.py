@@ -1,0 +1,373 @@
+"""Engine: the thin PyTorch / C-ABI layer that hands batched realization parameters to the
+sm_100a kernels (liboneka_b200.so).
+
+PyTorch is plumbing here: device memory (tensors), the CUDA stream, and torch.distributed
+(NCCL) for the one collective of the path -- the sum of the per-GPU integer count grids.
+All compute is in onekapy_b200/csrc/*.cu behind include/oneka_b200.h.
+
+There is NO CPU fallback: constructing an Engine without a usable B200 raises.
+
+Reference map (file:line under the reference tree):
+  start_ring()      oneka/capturezone.py:110-115
+  Engine.capture    body of the realization loop, oneka/stochastic.py:220-265 ->
+                    oneka/capturezone.py:51-123 (R calls with weight 1.0, fixed lattice)
+  Engine.run        the above + choosing the lattice + cropping to the extents the reference's
+                    auto-expanding ProbabilityField would end with (probabilityfield.py:229-245)
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import ModelDesc, Lattice, Stats, OnekaError
+from .lattice import LatticeGeom, final_geometry
+
+__all__ = ["Engine", "FlowSpec", "RealizationParams", "start_ring", "default_engine", "OnekaError"]
+
+
+@dataclass
+class FlowSpec:
+    """Everything that is constant over a run (the non-random arguments of
+    create_stochastic_capturezone, oneka/stochastic.py:76-81)."""
+    well_xy: np.ndarray            # [nw, 2]
+    xtarget: float
+    ytarget: float
+    rtarget: float
+    npaths: int
+    duration: float
+    base: float
+    spacing: float
+    umbra: float
+    confined: bool
+    tol: float
+    maxstep: float
+    max_attempts: int = 0
+
+    def model_desc(self) -> ModelDesc:
+        return ModelDesc(nw=int(len(self.well_xy)), confined=int(bool(self.confined)), base=float(self.base),
+                         xo=float(self.xtarget), yo=float(self.ytarget), duration=float(self.duration),
+                         tol=float(self.tol), maxstep=float(self.maxstep), max_attempts=int(self.max_attempts))
+
+
+@dataclass
+class RealizationParams:
+    """Pre-sampled per-realization rows (oneka/stochastic.py:224-241)."""
+    q: np.ndarray       # [R, nw] well discharges
+    cond: np.ndarray    # [R] conductivity
+    poro: np.ndarray    # [R] porosity
+    thick: np.ndarray   # [R] thickness
+    coef: np.ndarray    # [R, 6] A..F
+
+    def __post_init__(self):
+        self.cond = np.ascontiguousarray(self.cond, dtype=np.float64).reshape(-1)
+        R = len(self.cond)
+        self.poro = np.ascontiguousarray(self.poro, dtype=np.float64).reshape(R)
+        self.thick = np.ascontiguousarray(self.thick, dtype=np.float64).reshape(R)
+        self.coef = np.ascontiguousarray(self.coef, dtype=np.float64).reshape(R, 6)
+        self.q = np.ascontiguousarray(self.q, dtype=np.float64).reshape(R, -1)
+
+    def __len__(self):
+        return len(self.cond)
+
+    def slice(self, r0, r1, step=1):
+        s = slice(r0, r1, step)
+        return RealizationParams(self.q[s], self.cond[s], self.poro[s], self.thick[s], self.coef[s])
+
+
+def start_ring(xtarget, ytarget, rtarget, npaths):
+    """Start points on the circle of radius rtarget + 1 m (oneka/capturezone.py:110-115).
+
+    Evaluated scalar by scalar with NumPy, as the reference does, so that cos/sin round
+    identically; the points are the same for every realization."""
+    STEPAWAY = 1.0
+    out = np.empty((npaths, 2), dtype=np.float64)
+    for i, theta in enumerate(np.linspace(0, 2 * np.pi, npaths + 1)[0:-1]):
+        out[i, 0] = (rtarget + STEPAWAY) * np.cos(theta) + xtarget
+        out[i, 1] = (rtarget + STEPAWAY) * np.sin(theta) + ytarget
+    return out
+
+
+def _ptr(t):
+    """Device (or pinned-host) pointer of a torch tensor / numpy array, or None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class DeviceParams:
+    """RealizationParams resident in HBM (torch tensors own the memory)."""
+
+    def __init__(self, torch, device, params: RealizationParams, well_xy, start_xy):
+        f64 = torch.float64
+        self.R = len(params)
+        self.q = torch.as_tensor(params.q, dtype=f64).to(device)
+        self.cond = torch.as_tensor(params.cond, dtype=f64).to(device)
+        self.poro = torch.as_tensor(params.poro, dtype=f64).to(device)
+        self.thick = torch.as_tensor(params.thick, dtype=f64).to(device)
+        self.coef = torch.as_tensor(params.coef, dtype=f64).to(device)
+        self.well_xy = torch.as_tensor(np.ascontiguousarray(well_xy, dtype=np.float64)).to(device)
+        self.start_xy = torch.as_tensor(np.ascontiguousarray(start_xy, dtype=np.float64)).to(device)
+
+
+class Engine:
+    """One context per GPU (oneka_ctx)."""
+
+    def __init__(self, device: Optional[int] = None, workspace_limit: Optional[int] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise OnekaError("no CUDA device visible: onekapy_b200 has no CPU fallback")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = torch
+        self.index = int(device)
+        self.device = torch.device("cuda", self.index)
+        torch.cuda.set_device(self.device)
+        self._L = _cabi.load()
+        self._h = _cabi.create(self.index)
+        self.use_stream(torch.cuda.current_stream(self.device))
+        if workspace_limit is not None:
+            _cabi.check(self._L.oneka_set_workspace_limit(self._h, int(workspace_limit)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.oneka_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_stream(self, stream):
+        """Enqueue on a torch.cuda.Stream (kernels then order with torch ops on that stream)."""
+        self._stream = stream
+        _cabi.check(self._L.oneka_set_stream(self._h, C.c_void_p(stream.cuda_stream)))
+
+    def synchronize(self):
+        _cabi.check(self._L.oneka_synchronize(self._h))
+
+    # -- bookkeeping ------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._L.oneka_launch_count(self._h))
+
+    def set_profiling(self, on):
+        _cabi.check(self._L.oneka_set_profiling(self._h, int(bool(on))))
+
+    def kernel_ms(self, reset=False):
+        a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        _cabi.check(self._L.oneka_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return dict(track_ms=a.value, flush_ms=b.value, track_launches=int(n.value))
+
+    def reset_stats(self):
+        _cabi.check(self._L.oneka_reset_stats(self._h))
+
+    def read_stats(self):
+        s = Stats()
+        _cabi.check(self._L.oneka_read_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def fp64_probe(self, iters=1 << 16):
+        t, ms = C.c_double(0), C.c_double(0)
+        _cabi.check(self._L.oneka_fp64_probe(self._h, int(iters), C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    # -- Model.compute_* at points (oneka/model.py:207-427) -----------------------------------
+    def eval_points(self, well_xy, q, base, cond, poro, thick, xo, yo, coef, pts):
+        """-> [npts, 8] = potential, Qx, Qy, Vx_confined, Vy_confined, head, Vx, Vy."""
+        well_xy = np.ascontiguousarray(well_xy, dtype=np.float64).reshape(-1, 2)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1)
+        coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(6)
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((len(pts), 8), dtype=np.float64)
+        m = ModelDesc(nw=len(q), confined=1, base=float(base), xo=float(xo), yo=float(yo), duration=1.0, tol=1.0,
+                      maxstep=1.0, max_attempts=0)
+        _cabi.check(self._L.oneka_eval_points_host(self._h, C.byref(m), well_xy.ctypes.data, q.ctypes.data,
+                                                   float(cond), float(poro), float(thick), coef.ctypes.data,
+                                                   len(pts), pts.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- uploads ----------------------------------------------------------------------------
+    def upload(self, spec: FlowSpec, params: RealizationParams, start_xy=None) -> DeviceParams:
+        if start_xy is None:
+            start_xy = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        if params.q.shape[1] != len(spec.well_xy):
+            raise ValueError("q has %d columns but the spec has %d wells" % (params.q.shape[1], len(spec.well_xy)))
+        return DeviceParams(self.torch, self.device, params, spec.well_xy, start_xy)
+
+    # -- compute_backtrace with stored vertices (oneka/capturezone.py:127-253) ------------------
+    def trace(self, spec: FlowSpec, dp: DeviceParams, max_verts=4096):
+        """-> dict(verts[R,P,max_verts,2], nverts[R,P], status[R,P], attempts[R,P]) as numpy."""
+        torch = self.torch
+        R, P = dp.R, int(dp.start_xy.shape[0])
+        verts = torch.zeros((R, P, max_verts, 2), dtype=torch.float64, device=self.device)
+        nverts = torch.zeros((R, P), dtype=torch.int32, device=self.device)
+        status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
+        attempts = torch.zeros((R, P), dtype=torch.int32, device=self.device)
+        m = spec.model_desc()
+        _cabi.check(self._L.oneka_trace(self._h, C.byref(m), _ptr(dp.well_xy), R, P, _ptr(dp.q), _ptr(dp.cond),
+                                        _ptr(dp.poro), _ptr(dp.thick), _ptr(dp.coef), _ptr(dp.start_xy),
+                                        int(max_verts), _ptr(verts), _ptr(nverts), _ptr(status), _ptr(attempts)))
+        self.synchronize()
+        return dict(verts=verts.cpu().numpy(), nverts=nverts.cpu().numpy(), status=status.cpu().numpy(),
+                    attempts=attempts.cpu().numpy())
+
+    # -- insert/register on given traces (oneka/probabilityfield.py:264-359) -------------------
+    def raster_traces(self, geom: LatticeGeom, umbra, traces, real_of=None, nreal=None):
+        """Rasterise host polylines on a fixed lattice -> uint32 counts[nrows, ncols] (numpy)."""
+        torch = self.torch
+        traces = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1, 2) for t in traces]
+        n = len(traces)
+        if real_of is None:
+            real_of = np.zeros(n, dtype=np.int32)
+        real_of = np.ascontiguousarray(real_of, dtype=np.int32)
+        if nreal is None:
+            nreal = int(real_of.max()) + 1 if n else 0
+        off = np.zeros(n + 1, dtype=np.int64)
+        for i, t in enumerate(traces):
+            off[i + 1] = off[i] + len(t)
+        verts = np.concatenate(traces, axis=0) if n else np.zeros((0, 2))
+        d_off = torch.as_tensor(off).to(self.device)
+        d_verts = torch.as_tensor(verts).to(self.device)
+        d_real = torch.as_tensor(real_of).to(self.device)
+        counts = torch.zeros((geom.nrows, geom.ncols), dtype=torch.int32, device=self.device)
+        lat = geom.as_lattice(umbra)
+        _cabi.check(self._L.oneka_raster_traces(self._h, C.byref(lat), n, _ptr(d_off), _ptr(d_verts), _ptr(d_real),
+                                                int(nreal), _ptr(counts)))
+        self.synchronize()
+        return counts.cpu().numpy().view(np.uint32)
+
+    # -- the hot path, device-resident ----------------------------------------------------------
+    def new_counts(self, geom: LatticeGeom):
+        return self.torch.zeros((geom.nrows, geom.ncols), dtype=self.torch.int32, device=self.device)
+
+    def capture(self, spec: FlowSpec, dp: DeviceParams, geom: Optional[LatticeGeom] = None, counts=None,
+                per_path=False, r0=0, r1=None):
+        """Enqueue track + rasterise + register for realizations [r0, r1) of `dp` (asynchronous).
+
+        geom/counts None -> tracking only.  Returns the per-path tensors (or None)."""
+        torch = self.torch
+        r1 = dp.R if r1 is None else r1
+        R, P = r1 - r0, int(dp.start_xy.shape[0])
+        end_xy = nverts = status = None
+        if per_path:
+            end_xy = torch.zeros((R, P, 2), dtype=torch.float64, device=self.device)
+            nverts = torch.zeros((R, P), dtype=torch.int32, device=self.device)
+            status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
+        m = spec.model_desc()
+        lat = geom.as_lattice(spec.umbra) if geom is not None else None
+        _cabi.check(self._L.oneka_capture(
+            self._h, C.byref(m), C.byref(lat) if lat is not None else None, _ptr(dp.well_xy), R, P,
+            _ptr(dp.q[r0:r1]), _ptr(dp.cond[r0:r1]), _ptr(dp.poro[r0:r1]), _ptr(dp.thick[r0:r1]), _ptr(dp.coef[r0:r1]),
+            _ptr(dp.start_xy), _ptr(counts) if (counts is not None and lat is not None) else None,
+            _ptr(end_xy), _ptr(nverts), _ptr(status)))
+        if per_path:
+            return dict(end_xy=end_xy, nverts=nverts, status=status)
+        return None
+
+    # -- the hot path, host buffers in / host grid out (what the drop-in layer calls) -------------
+    def capture_host(self, spec: FlowSpec, params: RealizationParams, geom: Optional[LatticeGeom], start_xy=None,
+                     per_path=False, counts_out=None):
+        """One synchronous call: H2D of the parameter rows, kernels, D2H of the count grid.
+
+        Arrays may be numpy or pinned torch CPU tensors.  Returns (counts uint32 numpy or None, stats, per-path)."""
+        if start_xy is None:
+            start_xy = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        start_xy = np.ascontiguousarray(start_xy, dtype=np.float64)
+        well_xy = np.ascontiguousarray(spec.well_xy, dtype=np.float64)
+        R, P = len(params), len(start_xy)
+        m = spec.model_desc()
+        lat = geom.as_lattice(spec.umbra) if geom is not None else None
+        counts = None
+        if geom is not None:
+            counts = counts_out if counts_out is not None else np.zeros((geom.nrows, geom.ncols), dtype=np.uint32)
+        end_xy = nverts = status = None
+        if per_path:
+            end_xy = np.zeros((R, P, 2))
+            nverts = np.zeros((R, P), dtype=np.int32)
+            status = np.zeros((R, P), dtype=np.uint8)
+        st = Stats()
+        _cabi.check(self._L.oneka_capture_host(
+            self._h, C.byref(m), C.byref(lat) if lat is not None else None, well_xy.ctypes.data, R, P,
+            _ptr(params.q), _ptr(params.cond), _ptr(params.poro), _ptr(params.thick), _ptr(params.coef),
+            start_xy.ctypes.data, _ptr(counts), _ptr(end_xy), _ptr(nverts), _ptr(status), C.byref(st)))
+        pp = dict(end_xy=end_xy, nverts=nverts, status=status) if per_path else None
+        return counts, st.as_dict(), pp
+
+    # -- the public flow -----------------------------------------------------------------------
+    def run(self, spec: FlowSpec, params: RealizationParams, pilot=256, margin=0.25, group=None, per_path=False):
+        """Capture-zone count grid for all realizations in `params` (this rank's shard when `group`
+        is a torch.distributed process group), on the extents the reference would end with.
+
+        1. pilot: tracking-only pass over <= `pilot` realizations -> bounding box (all of them
+           when R <= pilot, which makes the box exact);
+        2. lattice = reference lattice (anchored at target - spacing, probabilityfield.py:140-146)
+           expanded to the pilot box plus `margin` of its size on every side;
+        3. fused capture on that lattice; if any vertex fell outside it, grow and repeat once;
+        4. (multi-GPU) bounding boxes min/max-reduced, count grids summed with ONE allreduce;
+        5. crop to the reference's final extents (probabilityfield.py:229-245).
+
+        Returns dict(counts uint32[nrows,ncols], geom LatticeGeom, total_weight, stats, per_path)."""
+        from . import parallel
+        torch = self.torch
+        R = len(params)
+        start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        dp = self.upload(spec, params, start)
+        # 1. pilot
+        self.reset_stats()
+        if R <= pilot:
+            self.capture(spec, dp)
+            exact = True
+        else:
+            step = R // pilot
+            sub = params.slice(0, step * pilot, step)
+            self.capture(spec, self.upload(spec, sub, start))
+            exact = False
+        bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, self.device if group is not None else None)
+        if group is not None and parallel.any_rank(not exact, group, self.device):
+            exact = False
+        if not np.all(np.isfinite(bbox)):
+            raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
+        pad = 0.0 if exact else margin
+        for attempt in range(3):
+            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+            grow = (bbox[0] - pad * w, bbox[1] + pad * w, bbox[2] - pad * h, bbox[3] + pad * h)
+            geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(*grow)
+            counts = self.new_counts(geom)
+            self.reset_stats()
+            pp = self.capture(spec, dp, geom, counts, per_path=per_path)
+            stats = self.read_stats()
+            true_bbox = parallel.reduce_bbox(stats["bbox"], group, self.device if group is not None else None)
+            if geom.strictly_contains(true_bbox):
+                break
+            bbox, pad = true_bbox, 0.0          # now exact: the second pass is guaranteed to fit
+        else:
+            raise OnekaError("lattice did not converge")
+        if group is not None:
+            parallel.allreduce_counts(counts, group)
+            total = parallel.sum_int(R, group, self.device)
+        else:
+            total = R
+        final = final_geometry(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget, true_bbox)
+        i0, j0 = geom.offset_of(final)
+        out = counts[i0:i0 + final.nrows, j0:j0 + final.ncols].contiguous().cpu().numpy().view(np.uint32)
+        if per_path:
+            pp = {k: v.cpu().numpy() for k, v in pp.items()}
+        return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
+
+
+_DEFAULT = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on cuda:LOCAL_RANK (created on first use; raises without a GPU)."""
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Engine()
+    return _DEFAULT

@@ -1,0 +1,89 @@
+"""Lattice geometry of the ProbabilityField (host side, integers and a handful of doubles).
+
+The reference grid is node-centred, anchored on the target well and grows one whole cell at
+a time by REPEATED addition/subtraction of the spacing (oneka/probabilityfield.py:140-146,
+229-245).  LatticeGeom reproduces exactly that arithmetic, so that a lattice grown in one go
+to a bounding box has the same xmin/xmax/ymin/ymax doubles the reference reaches after its
+sequence of per-trace expansions.
+"""
+import math
+from dataclasses import dataclass
+
+from ._cabi import Lattice
+
+
+@dataclass(frozen=True)
+class LatticeGeom:
+    deltax: float
+    deltay: float
+    xmin: float
+    xmax: float
+    ymin: float
+    ymax: float
+    nrows: int
+    ncols: int
+
+    # -- constructors ---------------------------------------------------------------------------
+    @staticmethod
+    def anchored(deltax, deltay, xo, yo):
+        """3 x 3 nodes centred on (xo, yo): probabilityfield.py:140-146."""
+        if deltax <= 0 or deltay <= 0:
+            raise ValueError("<deltax>, <deltay> must be > 0.")
+        return LatticeGeom(deltax, deltay, xo - deltax, xo + deltax, yo - deltay, yo + deltay, 3, 3)
+
+    @staticmethod
+    def of_field(pf):
+        return LatticeGeom(pf.deltax, pf.deltay, pf.xmin, pf.xmax, pf.ymin, pf.ymax, int(pf.nrows), int(pf.ncols))
+
+    # -- probabilityfield.py:229-245 ------------------------------------------------------------------
+    def expanded(self, xmin, xmax, ymin, ymax):
+        """Grow by whole cells until the box is STRICTLY inside; returns the new geometry."""
+        return self.expanded_with_shift(xmin, xmax, ymin, ymax)[0]
+
+    def expanded_with_shift(self, xmin, xmax, ymin, ymax):
+        """-> (geometry, rshift, cshift): rows/columns added below/left (probabilityfield.py:225-245)."""
+        if xmin > xmax or ymin > ymax:
+            raise ValueError("min must be <= max")
+        if not all(math.isfinite(v) for v in (xmin, xmax, ymin, ymax)):
+            raise ValueError("non-finite bounding box")
+        x0, x1, y0, y1 = self.xmin, self.xmax, self.ymin, self.ymax
+        nrows, ncols = self.nrows, self.ncols
+        rshift = cshift = 0
+        while xmin <= x0:
+            x0 -= self.deltax
+            ncols += 1
+            cshift += 1
+        while xmax >= x1:
+            x1 += self.deltax
+            ncols += 1
+        while ymin <= y0:
+            y0 -= self.deltay
+            nrows += 1
+            rshift += 1
+        while ymax >= y1:
+            y1 += self.deltay
+            nrows += 1
+        return LatticeGeom(self.deltax, self.deltay, x0, x1, y0, y1, nrows, ncols), rshift, cshift
+
+    # -- queries ------------------------------------------------------------------------------------
+    def strictly_contains(self, bbox):
+        """True when expand(bbox) would be a no-op (every vertex strictly inside the outer nodes)."""
+        return (bbox[0] > self.xmin) and (bbox[1] < self.xmax) and (bbox[2] > self.ymin) and (bbox[3] < self.ymax)
+
+    def offset_of(self, inner):
+        """(row, col) index of `inner`'s node (0, 0) in this lattice (same anchor, same spacing)."""
+        j0 = int(round((inner.xmin - self.xmin) / self.deltax))
+        i0 = int(round((inner.ymin - self.ymin) / self.deltay))
+        if i0 < 0 or j0 < 0 or i0 + inner.nrows > self.nrows or j0 + inner.ncols > self.ncols:
+            raise ValueError("inner lattice is not contained in this one")
+        return i0, j0
+
+    def as_lattice(self, umbra) -> Lattice:
+        return Lattice(xmin=float(self.xmin), ymin=float(self.ymin), deltax=float(self.deltax),
+                       deltay=float(self.deltay), nrows=int(self.nrows), ncols=int(self.ncols), umbra=float(umbra))
+
+
+def final_geometry(deltax, deltay, xo, yo, bbox):
+    """The extents the reference's auto-expanding field ends with when the union of all trace
+    bounding boxes is `bbox` (successive expansions commute with one expansion to the union)."""
+    return LatticeGeom.anchored(deltax, deltay, xo, yo).expanded(*bbox)

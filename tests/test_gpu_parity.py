@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI.
+
+Bars
+  * rasterisation (insert/register on given traces): BIT-EXACT against the executed reference's
+    grids (tests/golden) and against the oracle on random tracks;
+  * traces: same number of vertices per path, every vertex within 1e-6 relative position
+    (north_star's tolerance; observed ~1e-12);
+  * fused capture on a fixed lattice: attempts/steps totals equal the oracle's, count grid equal
+    cell by cell (the differing-cell fraction is asserted to be 0 and printed);
+  * drop-in run (auto-expanding reference): final geometry identical; the grid is a superset of the
+    reference's with a differing-cell fraction below 2e-3 (order-dependent clipping).
+"""
+import numpy as np
+import pytest
+
+from helpers import scal, geom, traces_of
+
+pytestmark = pytest.mark.gpu
+
+CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz"]
+POS_RTOL = 1e-6       # BASELINE.json north_star: endpoints within 1e-6 relative position
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from onekapy_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def spec_of(g):
+    from onekapy_b200.engine import FlowSpec, RealizationParams
+    s = scal(g)
+    spec = FlowSpec(well_xy=g["wells_xyr"][:, :2].copy(), xtarget=s["xt"], ytarget=s["yt"], rtarget=s["rt"],
+                    npaths=s["P"], duration=s["duration"], base=s["base"], spacing=s["spacing"], umbra=s["umbra"],
+                    confined=s["confined"], tol=s["tol"], maxstep=s["maxstep"])
+    par = RealizationParams(q=g["q"], cond=g["k"], poro=g["n"], thick=g["H"], coef=g["coef"])
+    return s, spec, par
+
+
+def fixed_geom(g, s):
+    from onekapy_b200.lattice import LatticeGeom
+    return LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"]).expanded(*g["lattice"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_library_loaded_and_device(eng):
+    import torch
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    tf, ms = eng.fp64_probe(1 << 14)
+    assert tf > 5.0, "FP64 probe reports %.2f TFLOP/s" % tf
+
+
+def test_model_known_answers(eng):
+    """reference tests/test_model.py:45-76 through the CUDA field functions."""
+    from onekapy_b200.host.model import Model
+    mo = Model(500.0, 1.0, 0.25, 100.0, [(100.0, 200.0, 1.0, 1000.0), (200.0, 100.0, 1.0, 1000.0)], 0.0, 0.0,
+               np.array([1.0, 1.0, 1.0, 1.0, 1.0, 500.0]))
+    assert np.isclose(mo.compute_potential(100.0, 100.0), 32165.8711977589, rtol=1.0e-6)
+    assert np.isclose(mo.compute_head(100.0, 100.0), 371.658711977589, rtol=1.0e-6)
+    assert np.allclose(mo.compute_discharge(120.0, 160.0), [-401.318309886184, -438.771830796713], rtol=1.0e-6)
+    assert np.allclose(mo.compute_velocity(100.0, 100.0), [-11.976338022763, -11.976338022763], rtol=1.0e-6)
+    assert np.allclose(mo.compute_velocity(120.0, 160.0), [-16.052732395447, -17.550873231869], rtol=1.0e-6)
+    assert np.allclose(mo.compute_velocity_confined(120.0, 160.0), [-16.052732395447, -17.550873231869], rtol=1.0e-6)
+
+
+def test_model_points_vs_reference(eng, golden):
+    from onekapy_b200.host.model import Model, AquiferError
+    g = golden("model_points.npz")
+    wells = [tuple(w) for w in g["wells"]]
+    for par, pts, ref in zip(g["par"], g["pts"], g["out"]):
+        base, k, n, H, xo, yo = par[:6]
+        mo = Model(base, k, n, H, wells, xo, yo, par[6:])
+        out = mo.evaluate(pts)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.allclose(out, ref, rtol=1e-12, atol=0, equal_nan=True)
+        dry = np.where(np.isnan(ref[:, 5]))[0]
+        for i in dry[:2]:
+            with pytest.raises(AquiferError):
+                mo.compute_head(*pts[i])
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_raster_insert_fixture_bit_exact(eng, golden):
+    """probabilityfield.insert + register on hand-made tracks (zero-length, axis-aligned, lattice-aligned
+    exact ties, micro segments, clipped by the lattice edge)."""
+    from onekapy_b200.lattice import LatticeGeom
+    g = golden("insert.npz")
+    tracks = traces_of(g)
+    for tag in "abc":
+        dx, dy, umbra = g["par_" + tag]
+        gm = LatticeGeom.anchored(dx, dy, 60.0, 60.0).expanded(0.0, 200.0, 0.0, 200.0)
+        ref = geom(g, "fixed_%s_" % tag)
+        assert (gm.xmin, gm.ymin, gm.nrows, gm.ncols) == (ref["xmin"], ref["ymin"], ref["nrows"], ref["ncols"])
+        counts = eng.raster_traces(gm, umbra, tracks, g["real_of"], 2)
+        assert np.array_equal(counts, g["fixed_%s_counts" % tag].astype(np.uint32)), tag
+
+
+def test_probabilityfield_methods_on_gpu(eng, golden):
+    """ProbabilityField.insert / rasterize / register (drop-in class) reproduce the reference's
+    auto-expanding and fixed results on the hand-made tracks."""
+    from onekapy_b200.host.probabilityfield import ProbabilityField
+    g = golden("insert.npz")
+    tracks = traces_of(g)
+    real_of = g["real_of"]
+    dx, dy, umbra = g["par_b"]
+    pf = ProbabilityField(dx, dy, 60.0, 60.0)
+    for r in (0, 1):
+        for t, rr in zip(tracks, real_of):
+            if rr == r:
+                pf.rasterize(list(t[:, 0]), list(t[:, 1]), umbra)
+        pf.register(1.0)
+    ref = geom(g, "auto_b_")
+    assert (pf.xmin, pf.xmax, pf.ymin, pf.ymax, pf.nrows, pf.ncols) == (ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"])
+    assert np.array_equal(pf.pgrid, g["auto_b_counts"].astype(float)) and pf.total_weight == 2.0
+    pf = ProbabilityField(dx, dy, 60.0, 60.0)
+    pf.expand(0.0, 200.0, 0.0, 200.0)
+    t = tracks[0]
+    for i in range(len(t) - 1):
+        pf.insert(t[i, 0], t[i, 1], t[i + 1, 0], t[i + 1, 1], umbra)
+    from oracle import oracle as O
+    of = O.Field(dx, dy, 60.0, 60.0)
+    of.expand(0.0, 200.0, 0.0, 200.0)
+    for i in range(len(t) - 1):
+        of.insert(t[i, 0], t[i, 1], t[i + 1, 0], t[i + 1, 1], umbra)
+    assert np.array_equal(pf.rgrid, of.rgrid)
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_raster_reference_traces_bit_exact(eng, golden, name):
+    """The executed reference's own vertices, rasterised on the GPU == the reference's fixed-lattice grid."""
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    tr = traces_of(g)
+    real_of = np.repeat(np.arange(len(par)), s["P"]).astype(np.int32)
+    counts = eng.raster_traces(gm, s["umbra"], tr, real_of, len(par))
+    ref = g["fixed_counts"].astype(np.uint32)
+    ndiff = np.count_nonzero(counts != ref)
+    print("%s: raster-only differing cells %d of %d nonzero" % (name, ndiff, np.count_nonzero(ref)))
+    assert ndiff == 0
+
+
+def test_raster_random_tracks_vs_oracle(eng):
+    """2000 random tracks, non-integer lattice, 5 realizations, including degenerate segments."""
+    from onekapy_b200.lattice import LatticeGeom
+    from oracle import oracle as O
+    rng = np.random.default_rng(123)
+    dx, dy, umbra = 1.7, 2.3, 6.1
+    tracks, real_of = [], []
+    for t in range(2000):
+        n = int(rng.integers(2, 40))
+        step = rng.uniform(-7, 7, size=(n, 2))
+        if t % 50 == 0:
+            step[n // 2] = 0.0                      # zero-length segment
+        if t % 70 == 0:
+            step[:, 1] = 0.0                        # horizontal track
+        tracks.append(np.cumsum(step, axis=0) + rng.uniform(50, 350, size=2))
+        real_of.append(t % 5)
+    gm = LatticeGeom.anchored(dx, dy, 200.0, 200.0).expanded(20.0, 380.0, 20.0, 380.0)
+    eng.reset_stats()
+    counts = eng.raster_traces(gm, umbra, tracks, np.array(real_of, dtype=np.int32), 5)
+    st = eng.read_stats()
+    of = O.Field(dx, dy, 200.0, 200.0)
+    of.expand(20.0, 380.0, 20.0, 380.0)
+    for r in range(5):
+        for t, rr in zip(tracks, real_of):
+            if rr == r:
+                for i in range(len(t) - 1):
+                    of.insert(t[i, 0], t[i, 1], t[i + 1, 0], t[i + 1, 1], umbra)
+        of.register(1.0)
+    assert (gm.nrows, gm.ncols) == (of.nrows, of.ncols)
+    assert np.array_equal(counts, of.pgrid.astype(np.uint32))
+    print("random tracks: %d segments, %d cells re-tested in exact FP64, %d clipped" % (st["steps"], st["exact_tests"], st["n_clipped"]))
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CAPTURES)
+def test_traces_vs_reference(eng, golden, name):
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    dp = eng.upload(spec, par)
+    out = eng.trace(spec, dp, max_verts=1024)
+    ref = traces_of(g)
+    worst = 0.0
+    for r in range(len(par)):
+        for p in range(s["P"]):
+            t = ref[r * s["P"] + p]
+            assert out["status"][r, p] == 0
+            assert out["nverts"][r, p] == len(t), (name, r, p)
+            v = out["verts"][r, p, :len(t)]
+            err = np.abs(v - t).max(axis=1) / np.maximum(np.abs(t).max(axis=1), 1.0)
+            worst = max(worst, err.max())
+    print("%s: max relative vertex error %.3e" % (name, worst))
+    assert worst < POS_RTOL
+
+
+def test_dry_aquifer_status(eng, golden):
+    """confined=False forward traces that hit potential <= 0: truncated at the same vertex as the reference."""
+    from onekapy_b200.engine import FlowSpec, RealizationParams
+    g = golden("unc_dry.npz")
+    base, k, n, H, xo, yo = g["par"]
+    dur, tol, maxstep = g["scal"]
+    spec = FlowSpec(well_xy=g["wells"][:, :2].copy(), xtarget=xo, ytarget=yo, rtarget=0.25, npaths=len(g["starts"]),
+                    duration=dur, base=base, spacing=1.0, umbra=1.0, confined=False, tol=tol, maxstep=maxstep)
+    par = RealizationParams(q=g["wells"][None, :, 3], cond=[k], poro=[n], thick=[H], coef=g["coef"][None, :])
+    dp = eng.upload(spec, par, g["starts"])
+    out = eng.trace(spec, dp, max_verts=512)
+    for p, (t, dry) in enumerate(zip(traces_of(g), g["terminated"])):
+        assert out["status"][0, p] == (1 if dry else 0)
+        assert out["nverts"][0, p] == len(t)
+        v = out["verts"][0, p, :len(t)]
+        assert np.abs(v - t).max() / np.abs(t).max() < POS_RTOL
+
+
+def test_max_attempt_guard(eng, golden):
+    g = golden("sto_basic.npz")
+    s, spec, par = spec_of(g)
+    spec.max_attempts = 50
+    out = eng.trace(spec, eng.upload(spec, par), max_verts=64)
+    assert (out["status"] == 2).all() and (out["attempts"] == 50).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CAPTURES)
+def test_fused_capture_fixed_lattice(eng, golden, name):
+    from oracle import oracle as O
+    from onekapy_b200.engine import start_ring
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    dp = eng.upload(spec, par)
+    counts = eng.new_counts(gm)
+    eng.reset_stats()
+    pp = eng.capture(spec, dp, gm, counts, per_path=True)
+    st = eng.read_stats()
+    got = counts.cpu().numpy().view(np.uint32)
+    ref = g["fixed_counts"].astype(np.uint32)
+    tr = traces_of(g)
+    assert np.array_equal(pp["nverts"].cpu().numpy().ravel(), [len(t) for t in tr])
+    assert st["steps"] == sum(len(t) - 1 for t in tr) and st["paths"] == len(tr) and st["n_not_ok"] == 0
+    end_ref = np.array([t[-1] for t in tr]).reshape(len(par), s["P"], 2)
+    rel = (np.abs(pp["end_xy"].cpu().numpy() - end_ref).max(axis=2) / np.abs(end_ref).max(axis=2)).max()
+    ndiff = np.count_nonzero(got != ref)
+    print("%s: endpoint max rel err %.3e; differing cells %d of %d nonzero (fraction %.2e); exact re-tests %d"
+          % (name, rel, ndiff, np.count_nonzero(ref), ndiff / max(1, np.count_nonzero(ref)), st["exact_tests"]))
+    assert rel < POS_RTOL
+    assert ndiff == 0
+    # bounding box reported by the kernel == bounding box of the reference's vertices (to rounding)
+    v = g["verts"]
+    bb = np.array(st["bbox"])
+    assert np.allclose(bb, [v[:, 0].min(), v[:, 0].max(), v[:, 1].min(), v[:, 1].max()], rtol=1e-9)
+    # oracle on the same lattice agrees too (this is what the bigger tests below rely on)
+    of = O.Field(s["spacing"], s["spacing"], s["xt"], s["yt"])
+    of.expand(*g["lattice"])
+    res = O.capture(of, 1, spec.well_xy, s["base"], s["xt"], s["yt"], s["confined"], par.q, par.cond, par.poro,
+                    par.thick, par.coef, start_ring(s["xt"], s["yt"], s["rt"], s["P"]), s["duration"], s["umbra"],
+                    s["tol"], s["maxstep"])
+    assert res["attempts"] == st["attempts"]
+    assert np.array_equal(of.pgrid.astype(np.uint32), got)
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_run_vs_auto_expanding_reference(eng, golden, name):
+    """Engine.run (pilot -> lattice -> capture -> crop) against the reference left auto-expanding."""
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    res = eng.run(spec, par)
+    ref = geom(g, "auto_")
+    gm = res["geom"]
+    assert (gm.xmin, gm.xmax, gm.ymin, gm.ymax, gm.nrows, gm.ncols) == (ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"])
+    assert res["total_weight"] == ref["total_weight"]
+    got, want = res["counts"], g["auto_counts"].astype(np.uint32)
+    assert np.all(got >= want)                     # order-dependent clipping only ever drops cells
+    ndiff = np.count_nonzero(got != want)
+    frac = ndiff / np.count_nonzero(want)
+    print("%s: drop-in differing cells %d of %d nonzero (fraction %.2e)" % (name, ndiff, np.count_nonzero(want), frac))
+    assert frac < 2e-3 or ndiff < 64
+
+
+def test_run_with_subsampled_pilot(eng, golden):
+    """pilot < R: the lattice comes from a subsample + margin; result must not depend on it."""
+    g = golden("sto_basic.npz")
+    s, spec, par = spec_of(g)
+    a = eng.run(spec, par)
+    b = eng.run(spec, par, pilot=2, margin=0.0)      # margin 0 forces the grow-and-repeat branch
+    c = eng.run(spec, par, pilot=3, margin=0.5)
+    for r in (b, c):
+        assert r["geom"] == a["geom"] and np.array_equal(r["counts"], a["counts"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_dropin_api(eng, golden):
+    """oneka.deterministic / oneka.stochastic / oneka.capturezone keep their signatures."""
+    import oneka.deterministic as det
+    import oneka.stochastic as sto
+    import oneka.capturezone as cz
+    from oneka.model import Model
+    from oneka.probabilityfield import ProbabilityField
+    from onekapy_b200 import problems
+    from onekapy_b200.host.utilities import filter_obs
+
+    g = golden("det_basic.npz")
+    pb = problems.load("basic_deterministic")
+    obs = filter_obs(pb["observations"], pb["wells"], pb["buffer"])
+    pf = det.create_deterministic_capturezone(pb["target"], 16, pb["duration"], pb["base"], pb["c_dist"], pb["p_dist"],
+                                              pb["t_dist"], pb["wells"], obs, pb["spacing"], pb["umbra"], pb["confined"],
+                                              pb["tol"], pb["maxstep"])
+    ref = geom(g, "auto_")
+    assert isinstance(pf, ProbabilityField)
+    assert (pf.xmin, pf.xmax, pf.ymin, pf.ymax, pf.nrows, pf.ncols, pf.total_weight) == (
+        ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"], 1.0)
+    want = g["auto_counts"].astype(float)
+    assert pf.pgrid.dtype == np.float64 and pf.rgrid.dtype == bool and not pf.rgrid.any()
+    assert np.all(pf.pgrid >= want) and np.count_nonzero(pf.pgrid != want) / np.count_nonzero(want) < 2e-3
+
+    # compute_capturezone with a closure of the reference's shape (stochastic.py:253-256) on a caller-owned field
+    wells = [[w[0], w[1], w[2], q] for w, q in zip(pb["wells"], g["q"][0])]
+    mo = Model(pb["base"], g["k"][0], g["n"][0], g["H"][0], wells)
+    xt, yt, rt = pb["wells"][0][0:3]
+    mo.xo, mo.yo, mo.coef = xt, yt, g["coef"][0]
+
+    def feval(xy):
+        Vx, Vy = mo.compute_velocity_confined(xy[0], xy[1])
+        return np.array([-Vx, -Vy])
+
+    pf2 = ProbabilityField(pb["spacing"], pb["spacing"], xt, yt)
+    cz.compute_capturezone(xt, yt, rt, 16, pb["duration"], pf2, pb["umbra"], 1.0, pb["tol"], pb["maxstep"], feval)
+    assert np.array_equal(pf2.pgrid, pf.pgrid) and pf2.total_weight == 1.0
+    cz.compute_capturezone(xt, yt, rt, 16, pb["duration"], pf2, pb["umbra"], 0.5, pb["tol"], pb["maxstep"], feval)
+    assert pf2.total_weight == 1.5 and pf2.pgrid.max() == 1.5
+
+    # compute_backtrace returns the vertex list
+    start = traces_of(g)[3][0]
+    v = cz.compute_backtrace(start[0], start[1], pb["duration"], pb["tol"], pb["maxstep"], feval)
+    t = traces_of(g)[3]
+    assert len(v) == len(t) and np.abs(np.array(v) - t).max() / np.abs(t).max() < POS_RTOL
+    # the closure itself still evaluates (through the CUDA field function)
+    assert np.allclose(feval(np.array(start)), cz.BacktraceVelocity(mo, True)(np.array(start)))
+    with pytest.raises(TypeError):
+        cz.compute_backtrace(0.0, 0.0, 1.0, 1.0, 1.0, lambda xy: xy)
+
+    # stochastic driver: signature, type, totals
+    pb = problems.load("basic")
+    obs = filter_obs(pb["observations"], pb["wells"], pb["buffer"])
+    np.random.seed(7)
+    pfs = sto.create_stochastic_capturezone(pb["target"], 10, pb["duration"], 6, pb["base"], pb["c_dist"], pb["p_dist"],
+                                            pb["t_dist"], pb["wells"], obs, pb["spacing"], pb["umbra"], pb["confined"],
+                                            pb["tol"], pb["maxstep"], rng=np.random.default_rng(7))
+    gs = golden("sto_basic.npz")
+    refs = geom(gs, "auto_")
+    assert pfs.total_weight == 6.0 and pfs.pgrid.max() == 6.0
+    # same seeded rows as the fixture (coef equal to ~1e-9 relative) -> same geometry, near-identical grid
+    assert (pfs.nrows, pfs.ncols, pfs.xmin, pfs.ymin) == (refs["nrows"], refs["ncols"], refs["xmin"], refs["ymin"])
+    assert np.count_nonzero(pfs.pgrid != gs["auto_counts"]) / np.count_nonzero(gs["auto_counts"]) < 5e-3
+
+
+def test_bad_arguments(eng, golden):
+    from onekapy_b200.engine import OnekaError
+    from onekapy_b200.lattice import LatticeGeom
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    dp = eng.upload(spec, par)
+    spec.tol = 0.0
+    with pytest.raises(OnekaError):
+        eng.capture(spec, dp)
+    spec.tol = 1.0
+    spec.maxstep = -1.0
+    with pytest.raises(OnekaError):
+        eng.capture(spec, dp)
+    spec.maxstep = 10.0
+    eng2 = type(eng)(0, workspace_limit=16)
+    with pytest.raises(OnekaError):
+        eng2.capture(spec, dp, fixed_geom(g, s), eng2.new_counts(fixed_geom(g, s)))
+    eng2.close()
