@@ -19,7 +19,7 @@ recorded inputs are stored, as small .npz files:
   sto_basic.npz      stochastic path on pre-sampled parameters (data/basic.py), 6 x 10: traces + grids (auto + fixed lattice)
   sto_perham.npz     same for data/perham.py, 2 x 20
   unc_basic.npz      confined=False path, 3 x 8 (+ a trace that raises AquiferError)
-  fwd_basic.npz      negative duration (forward tracking) traces
+  fwd_basic.npz      negative duration (forward tracking) from injection wells (data/basic.py, discharges negated)
 
 Sampling follows `oneka/stochastic.py:220-241` line by line, except that the A-F draw
 uses ONE seeded Generator instead of a fresh unseeded one per realization (`:241`),
@@ -281,8 +281,20 @@ def gen_insert():
     save("insert.npz", offsets=off, verts=verts, real_of=real_of, **out)
 
 
-def gen_capture(name, modname, nreal, npaths, seed, confined=None, deterministic=False, duration=None):
-    m = importlib.import_module("data." + modname)
+def injection_variant(modname):
+    """data/<modname>.py with every well turned into an INJECTION well (discharges negated).
+    Forward tracking (negative duration) from the ring of an injection well is well-posed;
+    from a pumping well it runs into the singularity and is chaotic at rounding level."""
+    import types
+    m0 = importlib.import_module("data." + modname)
+    m = types.SimpleNamespace(**{k: getattr(m0, k) for k in dir(m0) if k.isupper()})
+    m.WELLS = [(w[0], w[1], w[2], tuple(-t for t in reversed(w[3])) if isinstance(w[3], tuple) else -w[3])
+               for w in m0.WELLS]
+    return m
+
+
+def gen_capture(name, modname, nreal, npaths, seed, confined=None, deterministic=False, duration=None, injection=False):
+    m = injection_variant(modname) if injection else importlib.import_module("data." + modname)
     confined = m.CONFINED if confined is None else confined
     if deterministic:
         # oneka/deterministic.py:185-199
@@ -380,6 +392,6 @@ if __name__ == "__main__":
     if "unc" in which:
         gen_capture("unc_basic.npz", "basic", 3, 8, seed=13, confined=False)
     if "fwd" in which:
-        gen_capture("fwd_basic.npz", "basic", 2, 6, seed=21, duration=-1500.0)
+        gen_capture("fwd_basic.npz", "basic", 2, 6, seed=21, duration=-1500.0, injection=True)
     if "dry" in which:
         gen_unconfined_dry()
