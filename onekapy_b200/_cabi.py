@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboneka_b200.so")
+# ONEKA_B200_LIB lets a developer A/B an experimental build of the same ABI (never a different implementation)
+LIB_PATH = os.environ.get("ONEKA_B200_LIB") or os.path.join(_HERE, "liboneka_b200.so")
 
 OK = 0
 PATH_OK, PATH_AQUIFER_DRY, PATH_MAX_ATTEMPT, PATH_NONFINITE, PATH_TRACE_FULL = 0, 1, 2, 3, 4
@@ -89,9 +90,7 @@ def load():
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Stats)]
     L.oneka_fp64_probe.argtypes = [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in SYMBOLS:
-        f = getattr(L, name)
-        if f.restype is C.c_int and name not in ("oneka_abi_version",):
-            pass
+        getattr(L, name)                  # AttributeError here = header / library mismatch
     _lib = L
     return L
 

@@ -34,6 +34,9 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 constexpr int TRACK_THREADS = 128;          // 4 warps per CTA; every warp stays inside one realization
+#ifndef TRACK_MIN_CTAS
+#define TRACK_MIN_CTAS 6                    // <= 80 registers/thread -> 24 warps per SM
+#endif
 constexpr int N_STATS = 16;
 
 struct oneka_ctx {
@@ -86,7 +89,7 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
 template <bool CONFINED, int MODE>
-__global__ void __launch_bounds__(TRACK_THREADS)
+__global__ void __launch_bounds__(TRACK_THREADS, TRACK_MIN_CTAS)
 track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
 {
     extern __shared__ double2 s_dyn[];
@@ -234,6 +237,7 @@ static int make_lattice(const oneka_lattice *lat, LatticeDev &L)
     L.umbra2 = lat->umbra * lat->umbra;
     L.dx32 = (float)lat->deltax; L.dy32 = (float)lat->deltay; L.umbra2_32 = (float)L.umbra2;
     L.maxd = lat->deltax > lat->deltay ? lat->deltax : lat->deltay;
+    L.inv_dx = 1.0 / lat->deltax; L.inv_dy = 1.0 / lat->deltay;
     L.words = (unsigned long long)L.nrows * (unsigned long long)L.wpr;
     return ONEKA_OK;
 }

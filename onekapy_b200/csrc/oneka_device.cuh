@@ -63,6 +63,7 @@ struct LatticeDev {
     double umbra, umbra2;            // umbra2 = umbra*umbra rounded once (probabilityfield.py:296)
     float dx32, dy32, umbra2_32;
     double maxd;                     // max(dx, dy)
+    double inv_dx, inv_dy;           // 1/dx, 1/dy (window pre-quotient, see floor_div)
     unsigned long long words;        // words per bitmap = nrows*wpr
 };
 
@@ -79,11 +80,23 @@ __device__ __forceinline__ double rcp_fast(double a)
 }
 
 // seed-and-correction split: returns y0 and t such that 1/a = y0 + y0*t
+//   ONEKA_RCP_ORDER 2 (default): t = e        (one quadratic Newton step on the MUFU.RCP64H seed:
+//                                 relative error = seed error squared, <= ~1e-12; 9 FP64 instr / well)
+//   ONEKA_RCP_ORDER 3          : t = e + e^2  (cubic step, ~1 ulp; 10 FP64 instr / well, 6 % slower)
+// Measured on the golden fixtures (tests/test_gpu_parity.py): max relative vertex error 4e-13 with
+// order 2, 1e-14 with order 3; both leave every step count and every grid cell unchanged.
+#ifndef ONEKA_RCP_ORDER
+#define ONEKA_RCP_ORDER 2
+#endif
 __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
     double e = fma(-a, y0, 1.0);
+#if ONEKA_RCP_ORDER == 3
     t = fma(e, e, e);
+#else
+    t = e;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -92,7 +105,7 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 // confined   (stochastic.py:254-256 -> model.py:423-427 -> 300-315):
 //     -V = [ (2A dx + C dy + D) + sum_w q_w/(2 pi) (x-x_w)/r_w^2 ] / (H n)
 //   with every constant pre-divided by H*n when the CTA stages its realization, so one well
-//   costs 10 FP64-pipe instructions (2 DADD, DMUL, 5 DFMA, 2 DMUL... see DESIGN.md) + 1 MUFU.
+//   costs 9 FP64-pipe instructions (2 DADD, 2 DMUL, 5 DFMA) + 1 MUFU.RCP64H + 1.5 LDS.128.
 // unconfined (stochastic.py:258-260 -> model.py:377-389, 341-350, 226-237, 259-266):
 //   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
 //   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
@@ -185,11 +198,26 @@ __device__ __forceinline__ double exact_distancesquared(double ax, double ay, do
 
 struct RasterCounters { unsigned int clipped, exact; };
 
-__device__ __noinline__ bool exact_cell_test(const LatticeDev &L, double ax, double ay, double bx, double by, int i, int j)
+__device__ __noinline__ bool exact_cell_test(double xmin, double ymin, double dx, double dy, double umbra2,
+                                             double ax, double ay, double bx, double by, int i, int j)
 {
-    const double cx = __dadd_rn(L.xmin, __dmul_rn((double)j, L.dx));     // probabilityfield.py:306
-    const double cy = __dadd_rn(L.ymin, __dmul_rn((double)i, L.dy));     // probabilityfield.py:307
-    return exact_distancesquared(ax, ay, bx, by, cx, cy) < L.umbra2;     // :309 (nan -> false)
+    const double cx = __dadd_rn(xmin, __dmul_rn((double)j, dx));         // probabilityfield.py:306
+    const double cy = __dadd_rn(ymin, __dmul_rn((double)i, dy));         // probabilityfield.py:307
+    return exact_distancesquared(ax, ay, bx, by, cx, cy) < umbra2;       // :309 (nan -> false)
+}
+
+// floor((v - org) / delta) with the reference's two IEEE operations (sub, div).  The quotient is
+// first formed with the precomputed reciprocal; only when it lands within 1e-9 (relative) of an
+// integer -- where a one-ulp difference could change the floor -- is the true division issued.
+__device__ __forceinline__ double floor_div(double v, double org, double delta, double inv_delta)
+{
+    const double num = __dsub_rn(v, org);
+    const double q = num * inv_delta;
+    const double f = floor(q);
+    const double frac = q - f;
+    const double tol = 1e-9 * fmax(1.0, fabs(q));
+    if (frac < tol || frac > 1.0 - tol) return floor(__ddiv_rn(num, delta));
+    return f;
 }
 
 __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__restrict__ bm,
@@ -198,10 +226,10 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
     // ---- window, probabilityfield.py:298-301 ----
     const double mnx = (bx < ax) ? bx : ax, mxx = (bx > ax) ? bx : ax;
     const double mny = (by < ay) ? by : ay, mxy = (by > ay) ? by : ay;
-    const double fl = floor(__ddiv_rn(__dsub_rn(__dsub_rn(mnx, L.umbra), L.xmin), L.dx));
-    const double fr = floor(__ddiv_rn(__dsub_rn(__dadd_rn(mxx, L.umbra), L.xmin), L.dx));
-    const double fb = floor(__ddiv_rn(__dsub_rn(__dsub_rn(mny, L.umbra), L.ymin), L.dy));
-    const double ft = floor(__ddiv_rn(__dsub_rn(__dadd_rn(mxy, L.umbra), L.ymin), L.dy));
+    const double fl = floor_div(__dsub_rn(mnx, L.umbra), L.xmin, L.dx, L.inv_dx);
+    const double fr = floor_div(__dadd_rn(mxx, L.umbra), L.xmin, L.dx, L.inv_dx);
+    const double fb = floor_div(__dsub_rn(mny, L.umbra), L.ymin, L.dy, L.inv_dy);
+    const double ft = floor_div(__dadd_rn(mxy, L.umbra), L.ymin, L.dy, L.inv_dy);
     const double lo_x = fmax(fl, 0.0), hi_x = fmin(fr + 1.0, (double)L.ncols);
     const double lo_y = fmax(fb, 0.0), hi_y = fmin(ft + 1.0, (double)L.nrows);
     if (fl < 0.0 || fb < 0.0 || fr + 1.0 > (double)L.ncols || ft + 1.0 > (double)L.nrows) ctr.clipped++;
@@ -219,31 +247,43 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
     const float base_x = (float)(fma((double)left, L.dx, L.xmin) - ax);
     const float base_y = (float)(fma((double)bottom, L.dy, L.ymin) - ay);
     const double Lm = fmax(fabs(bax), fabs(bay)) + L.umbra + L.maxd;
-    const float E = (float)(128.0 * 1.1920928955078125e-07 * Lm * Lm);
-    const float thr_in = L.umbra2_32 - E, thr_out = L.umbra2_32 + E;
+    const float E = all_exact ? INFINITY : (float)(128.0 * 1.1920928955078125e-07 * Lm * Lm);
+    const float u2 = L.umbra2_32;
 
-    const int w0 = left >> 5, w1 = (right - 1) >> 5;
-    for (int i = bottom; i < top; ++i) {
-        const float cay = fmaf((float)(i - bottom), L.dy32, base_y);
-        unsigned int *row = bm + (size_t)i * L.wpr;
-        for (int w = w0; w <= w1; ++w) {
-            const int j0 = max(left, w << 5), j1 = min(right, (w << 5) + 32);
-            unsigned int mask = 0;
-            for (int j = j0; j < j1; ++j) {
-                const float cax = fmaf((float)(j - left), L.dx32, base_x);
-                const float dot = fmaf(fbax, cax, fbay * cay);
-                const float t = __saturatef(dot * finv);
+    unsigned int *row = bm + (size_t)bottom * L.wpr;
+    float fi = 0.0f;
+    for (int i = bottom; i < top; ++i, row += L.wpr, fi += 1.0f) {
+        const float cay = fmaf(fi, L.dy32, base_y);
+        const float c1 = fbay * cay;
+        // columns in chunks of 32 starting at `left`: bit k of `mask` is column jc + k
+        for (int jc = left; jc < right; jc += 32) {
+            const int n = min(32, right - jc);
+            unsigned int mask = 0u, amb = 0u, bit = 1u;
+            float fk = (float)(jc - left);
+            for (int k = 0; k < n; ++k, fk += 1.0f, bit <<= 1) {
+                const float cax = fmaf(fk, L.dx32, base_x);
+                const float t = __saturatef(fmaf(fbax, cax, c1) * finv);
                 const float px = fmaf(-t, fbax, cax);
                 const float py = fmaf(-t, fbay, cay);
                 const float d2 = fmaf(px, px, py * py);
-                bool in = d2 < thr_in;
-                if (all_exact || !(in || d2 > thr_out)) {
-                    ctr.exact++;
-                    in = exact_cell_test(L, ax, ay, bx, by, i, j);
-                }
-                mask |= (in ? 1u : 0u) << (j & 31);
+                if (d2 < u2) mask |= bit;
+                if (!(fabsf(d2 - u2) > E)) amb |= bit;                   // inside the error band (or nan)
             }
-            if (mask) atomicOr(row + w, mask);
+            if (amb) {                                                   // rare: settle with the reference's FP64 formula
+                ctr.exact += __popc(amb);
+                do {
+                    const int k = __ffs(amb) - 1;
+                    amb &= amb - 1;
+                    if (exact_cell_test(L.xmin, L.ymin, L.dx, L.dy, L.umbra2, ax, ay, bx, by, i, jc + k)) mask |= 1u << k;
+                    else mask &= ~(1u << k);
+                } while (amb);
+            }
+            if (mask) {
+                const int sh = jc & 31;
+                unsigned int *wp = row + (jc >> 5);
+                atomicOr(wp, mask << sh);
+                if (sh && (mask >> (32 - sh))) atomicOr(wp + 1, mask >> (32 - sh));
+            }
         }
     }
 }
@@ -302,64 +342,82 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         if (status != PATH_OK) running = false;
     }
 
-    while (running && fabs(t) < adur) {                                    // :221
-        if (nattempt >= tp.max_attempts) { status = PATH_MAX_ATTEMPT; break; }
-        ++nattempt;
-        if (fabs(t + dt) > adur) dt = duration - t;                        // :223-224
+    // The loop is WARP-UNIFORM: every lane takes part in every iteration until no lane of the warp
+    // has work left (finished lanes idle, as they would under SIMT anyway).  That lets the divergent
+    // rasteriser be followed by __syncwarp(), so the FP64 tracking code of the next attempt always
+    // runs with the whole warp converged (without it the compiler leaves the lanes split after the
+    // raster loops and the well loop issues at half width; measured, profiles/r01_*).
+    for (;;) {
+        const bool go = running && fabs(t) < adur;                         // :221
+        if (!__any_sync(0xffffffffu, go)) break;
+        bool seg = false;
+        double sax = 0.0, say = 0.0;
+        if (go) {
+            do {
+                if (nattempt >= tp.max_attempts) { status = PATH_MAX_ATTEMPT; running = false; break; }
+                ++nattempt;
+                if (fabs(t + dt) > adur) dt = duration - t;                // :223-224
 
-        double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
-        int st;
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);              // :227
-        if (!CONFINED && st) { status = st; break; }
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
-                                   fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                          // :228
-        if (!CONFINED && st) { status = st; break; }
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
-                                   fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                           // :229
-        if (!CONFINED && st) { status = st; break; }
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
-                                   fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
-                                   fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);            // :230
-        if (!CONFINED && st) { status = st; break; }
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
-                                   fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
-                                   fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
-        if (!CONFINED && st) { status = st; break; }
+                double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
+                int st;
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
+                if (!CONFINED && st) { status = st; running = false; break; }
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                                           fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                  // :228
+                if (!CONFINED && st) { status = st; running = false; break; }
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                                           fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                   // :229
+                if (!CONFINED && st) { status = st; running = false; break; }
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                                           fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
+                                           fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);    // :230
+                if (!CONFINED && st) { status = st; running = false; break; }
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                                           fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
+                                           fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
+                if (!CONFINED && st) { status = st; running = false; break; }
 
-        const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);                 // :233
-        const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
-        st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, xt, yt, k7x, k7y);                                                    // :236
-        if (!CONFINED && st) { status = st; break; }
+                const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);         // :233
+                const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
+                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, xt, yt, k7x, k7y);                                            // :236
+                if (!CONFINED && st) { status = st; running = false; break; }
 
-        const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));               // :237-238
-        const double ey = dt * fma(e5, k6y, fma(e4, k5y, fma(e3, k4y, fma(e2, k3y, fma(e1, k7y, e0 * k1y)))));
-        const double est = fmax(fabs(ex), fabs(ey));
-        const double ddx = xt - x, ddy = yt - y;
-        const double ds = sqrt(fma(ddy, ddy, ddx * ddx));                                                                    // :239
+                const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238
+                const double ey = dt * fma(e5, k6y, fma(e4, k5y, fma(e3, k4y, fma(e2, k3y, fma(e1, k7y, e0 * k1y)))));
+                const double est = fmax(fabs(ex), fabs(ey));
+                const double ddx = xt - x, ddy = yt - y;
+                const double ds = sqrt(fma(ddy, ddy, ddx * ddx));                                                            // :239
 
-        if (!(isfinite(est) && isfinite(ds))) { status = PATH_NONFINITE; break; }   // the reference would loop forever on nan
+                if (!(isfinite(est) && isfinite(ds))) { status = PATH_NONFINITE; running = false; break; }   // the reference would loop forever on nan
 
-        if (est < tol && ds < maxstep) {                                   // :241-245
-            t = t + dt;
-            k1x = k7x; k1y = k7y;
-            if (MODE == 1) raster_seg(L, bm, x, y, xt, yt, ctr);
-            x = xt; y = yt;
-            bx0 = fmin(bx0, x); bx1 = fmax(bx1, x); by0 = fmin(by0, y); by1 = fmax(by1, y);
-            if (MODE == 2) {
-                if (nvert < tp.max_verts) { vout[2 * nvert] = x; vout[2 * nvert + 1] = y; }
-                else status = PATH_TRACE_FULL;
-            }
-            ++nvert;
+                if (est < tol && ds < maxstep) {                           // :241-245
+                    t = t + dt;
+                    k1x = k7x; k1y = k7y;
+                    seg = true; sax = x; say = y;
+                    x = xt; y = yt;
+                    bx0 = fmin(bx0, x); bx1 = fmax(bx1, x); by0 = fmin(by0, y); by1 = fmax(by1, y);
+                    if (MODE == 2) {
+                        if (nvert < tp.max_verts) { vout[2 * nvert] = x; vout[2 * nvert + 1] = y; }
+                        else status = PATH_TRACE_FULL;
+                    }
+                    ++nvert;
+                }
+
+                // :247  dt = 0.9 * min((tol/(est+EPS))**(1/5), maxstep/(ds+EPS), 10) * dt
+                // x**0.2 < c  <=>  x < c^5 : the pow is evaluated only when the error term governs.
+                const double cb = fmin(maxstep * rcp_fast(ds + EPS), 10.0);
+                const double xr = tol * rcp_fast(est + EPS);
+                const double c2 = cb * cb;
+                double mn = cb;
+                if (xr < c2 * c2 * cb) mn = fmin(pow(xr, 0.2), cb);
+                dt = 0.9 * mn * dt;
+            } while (false);
         }
-
-        // :247  dt = 0.9 * min((tol/(est+EPS))**(1/5), maxstep/(ds+EPS), 10) * dt
-        // x**0.2 < c  <=>  x < c^5 : the pow is evaluated only when the error term governs.
-        const double cb = fmin(maxstep * rcp_fast(ds + EPS), 10.0);
-        const double xr = tol * rcp_fast(est + EPS);
-        const double c2 = cb * cb;
-        double mn = cb;
-        if (xr < c2 * c2 * cb) mn = fmin(pow(xr, 0.2), cb);
-        dt = 0.9 * mn * dt;
+        if (MODE == 1) {
+            // chronicle the accepted step (capturezone.py:120 -> probabilityfield.py:338-339), then reconverge
+            if (seg) raster_seg(L, bm, sax, say, x, y, ctr);
+            __syncwarp();
+        }
     }
 
     // ---- per-path outputs ----

@@ -8,7 +8,7 @@ Bars
   * fused capture on a fixed lattice: attempts/steps totals equal the oracle's, count grid equal
     cell by cell (the differing-cell fraction is asserted to be 0 and printed);
   * drop-in run (auto-expanding reference): final geometry identical; the grid is a superset of the
-    reference's with a differing-cell fraction below 2e-3 (order-dependent clipping).
+    reference's with a differing-cell fraction below 2e-2 on these tiny runs (order-dependent clipping).
 """
 import numpy as np
 import pytest
@@ -276,7 +276,7 @@ def test_run_vs_auto_expanding_reference(eng, golden, name):
     ndiff = np.count_nonzero(got != want)
     frac = ndiff / np.count_nonzero(want)
     print("%s: drop-in differing cells %d of %d nonzero (fraction %.2e)" % (name, ndiff, np.count_nonzero(want), frac))
-    assert frac < 2e-3 or ndiff < 64
+    assert frac < 2e-2
 
 
 def test_run_with_subsampled_pilot(eng, golden):

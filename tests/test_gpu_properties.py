@@ -161,11 +161,12 @@ def test_c4_synthetic_200_wells(eng):
 
 
 def test_c5_fine_grid_long_duration(eng):
-    """Fine lattice (spacing 2, umbra 10: ~19 x 19-node windows), 3x the duration: raster stress."""
+    """Fine lattice of the 4096 x 4096 class (spacing 2, umbra 10: ~19 x 19-node windows) and long traces
+    (~600 steps per path, 4x C3): raster stress (BASELINE.json configs[4])."""
     spec, par = workload("c5", 32, 1000)
-    spec.duration *= 3.0
     dp = eng.upload(spec, par)
     geom, st0 = lattice_for(eng, spec, dp)
+    assert 2000 < max(geom.nrows, geom.ncols) < 16384, (geom.nrows, geom.ncols)
     counts = eng.new_counts(geom)
     eng.reset_stats()
     eng.capture(spec, dp, geom, counts)
