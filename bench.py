@@ -11,8 +11,8 @@ NCCL allreduce of the count grid) over one batch of pre-sampled realization rows
   c4            synthetic 200-well field, --realizations per GPU per step (default 2048) x 1000 paths
                 (BASELINE.json configs[3] is 1M realizations over 8 GPUs = 61 such steps per GPU)
   c1            data/basic.py, 100 x 100 (the reference's CPU-runnable case)
-  c5            data/basic_deterministic.py geometry (spacing 2, umbra 10 -> ~19x19-node windows),
-                256 realizations x 1000 paths: rasterisation stress
+  c5            data/basic.py field on a fine lattice (spacing 4, umbra 20 -> ~15x15-node windows, a
+                4096 x 4096-class grid), 256 realizations x 1000 paths: rasterisation stress
 
 metric = particle-steps/s = DOPRI5 attempts per second summed over all particles and GPUs;
 realizations/s is reported beside it.  Weak scaling: per-GPU work is fixed as N grows.
@@ -62,11 +62,11 @@ def make_workload(name, realizations, npaths, seed):
         P = npaths or 100
         label = "C1 basic (2 wells), %d realizations x %d paths per GPU per step" % (R, P)
     elif name == "c5":
-        pb = problems.load("basic_deterministic")
-        pb["c_dist"] = (35.0, 50.0, 75.0)
+        pb = problems.load("basic")
+        pb["spacing"], pb["umbra"] = 4.0, 20.0          # ~13 x 17 km of capture zones -> a 4096 x 4096-class lattice
         R = realizations or 256
         P = npaths or 1000
-        label = "C5 basic_deterministic geometry (spacing 2, umbra 10), %d realizations x %d paths per GPU per step" % (R, P)
+        label = "C5 basic field on a fine lattice (spacing 4, umbra 20: ~15x15-node windows, 4096^2-class grid), %d realizations x %d paths per GPU per step" % (R, P)
     else:
         raise SystemExit("unknown workload %r" % name)
     params = synthetic.sample_rows_fast(pb, R, seed)

@@ -245,6 +245,12 @@ class Engine:
 
     # -- the hot path, device-resident ----------------------------------------------------------
     def new_counts(self, geom: LatticeGeom):
+        need = 4 * int(geom.nrows) * int(geom.ncols)
+        free, _ = self.torch.cuda.mem_get_info(self.device)
+        if need > free:
+            raise OnekaError("count grid %d x %d needs %.1f GiB but %.1f GiB are free: the bounding box of the traces is "
+                             "implausibly large for this spacing (a realization ran away?)"
+                             % (geom.nrows, geom.ncols, need / 2**30, free / 2**30))
         return self.torch.zeros((geom.nrows, geom.ncols), dtype=self.torch.int32, device=self.device)
 
     def capture(self, spec: FlowSpec, dp: DeviceParams, geom: Optional[LatticeGeom] = None, counts=None,

@@ -161,8 +161,8 @@ def test_c4_synthetic_200_wells(eng):
 
 
 def test_c5_fine_grid_long_duration(eng):
-    """Fine lattice of the 4096 x 4096 class (spacing 2, umbra 10: ~19 x 19-node windows) and long traces
-    (~600 steps per path, 4x C3): raster stress (BASELINE.json configs[4])."""
+    """Fine lattice of the 4096 x 4096 class (spacing 4, umbra 20: ~15 x 15-node windows) and long traces
+    (~300 steps per path, 2x C3): raster stress (BASELINE.json configs[4])."""
     spec, par = workload("c5", 32, 1000)
     dp = eng.upload(spec, par)
     geom, st0 = lattice_for(eng, spec, dp)
