@@ -35,8 +35,11 @@ static int fail(int code, const char *fmt, ...)
 
 constexpr int TRACK_THREADS = 128;          // 4 warps per CTA; every warp stays inside one realization
 #ifndef TRACK_MIN_CTAS
-#define TRACK_MIN_CTAS 6                    // <= 80 registers/thread -> 24 warps per SM
+#define TRACK_MIN_CTAS 6                    // tracking only: <= 80 registers/thread -> 24 warps per SM
 #endif
+#ifndef FUSED_MIN_CTAS
+#define FUSED_MIN_CTAS 6                    // + rasteriser: 80 registers too (260 B of spills, all on the cold exact/fallback
+#endif                                      // paths); measured 6.19e9 attempts/s vs 5.92e9 at 4 CTAs/120 regs, 5.74e9 at 5/96
 constexpr int N_STATS = 16;
 
 struct oneka_ctx {
@@ -89,7 +92,7 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
 template <bool CONFINED, int MODE>
-__global__ void __launch_bounds__(TRACK_THREADS, TRACK_MIN_CTAS)
+__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
 track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
 {
     extern __shared__ double2 s_dyn[];
@@ -236,6 +239,7 @@ static int make_lattice(const oneka_lattice *lat, LatticeDev &L)
     L.umbra = lat->umbra;
     L.umbra2 = lat->umbra * lat->umbra;
     L.dx32 = (float)lat->deltax; L.dy32 = (float)lat->deltay; L.umbra2_32 = (float)L.umbra2;
+    L.umbra32 = (float)lat->umbra; L.inv_dx32 = 1.0f / L.dx32;
     L.maxd = lat->deltax > lat->deltay ? lat->deltax : lat->deltay;
     L.inv_dx = 1.0 / lat->deltax; L.inv_dy = 1.0 / lat->deltay;
     L.words = (unsigned long long)L.nrows * (unsigned long long)L.wpr;
