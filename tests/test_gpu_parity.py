@@ -181,6 +181,53 @@ def test_raster_random_tracks_vs_oracle(eng):
     print("random tracks: %d segments, %d cells re-tested in exact FP64, %d clipped" % (st["steps"], st["exact_tests"], st["n_clipped"]))
 
 
+@pytest.mark.parametrize("dx,dy,umbra,step,snap", [
+    (4.0, 4.0, 8.0, 9.0, 0.0),       # perham-like 7 x 7 windows
+    (2.0, 2.0, 10.0, 18.0, 0.0),     # basic_deterministic-like 19 x 19 windows
+    (0.5, 0.75, 9.0, 6.0, 0.0),      # > 32 columns per window: multi-word row masks
+    (10.0, 10.0, 4.0, 18.0, 0.0),    # umbra < spacing: most rows hold 0 or 1 node
+    (4.0, 4.0, 8.0, 9.0, 4.0),       # every vertex ON a lattice node: exact ties d2 == umbra^2, axis-aligned and 45-degree segments
+    (1.0, 3.0, 5.0, 0.02, 0.0),      # very short segments
+    (3.0, 3.0, 6.0, 12.0, 1e-3),     # vertices snapped to a 1 mm grid: near-horizontal / near-vertical segments
+])
+def test_raster_scanline_configs_vs_oracle(eng, dx, dy, umbra, step, snap):
+    """The scan-line rows (analytic interval per row) against the oracle's node-by-node insert, bit for bit."""
+    from onekapy_b200.lattice import LatticeGeom
+    from oracle import oracle as O
+    rng = np.random.default_rng(int(dx * 1000 + umbra * 10 + step))
+    tracks = []
+    for t in range(600):
+        n = int(rng.integers(2, 30))
+        ang = rng.uniform(0, 2 * np.pi) + np.cumsum(rng.normal(0, 0.4, size=n))
+        if t % 9 == 0:
+            ang = np.round(ang / (np.pi / 4)) * (np.pi / 4)              # axis-aligned / diagonal runs
+        if t % 13 == 0:
+            ang = rng.choice([0.0, np.pi]) + rng.normal(0, 1e-3, size=n)  # almost horizontal
+        seg = step * rng.uniform(0.2, 1.0, size=n)
+        v = np.cumsum(np.stack([seg * np.cos(ang), seg * np.sin(ang)], axis=1), axis=0) + rng.uniform(60, 140, size=2)
+        if snap > 0:
+            v = np.round(v / snap) * snap
+        tracks.append(v)
+    gm = LatticeGeom.anchored(dx, dy, 100.0, 100.0).expanded(40.0, 160.0, 40.0, 160.0)
+    real_of = (np.arange(len(tracks)) % 3).astype(np.int32)
+    eng.reset_stats()
+    counts = eng.raster_traces(gm, umbra, tracks, real_of, 3)
+    st = eng.read_stats()
+    of = O.Field(dx, dy, 100.0, 100.0)
+    of.expand(40.0, 160.0, 40.0, 160.0)
+    for r in range(3):
+        for t, rr in zip(tracks, real_of):
+            if rr == r:
+                for i in range(len(t) - 1):
+                    of.insert(t[i, 0], t[i, 1], t[i + 1, 0], t[i + 1, 1], umbra)
+        of.register(1.0)
+    ref = of.pgrid.astype(np.uint32)
+    ndiff = np.count_nonzero(counts != ref)
+    print("dx %.2f dy %.2f umbra %.1f: %d segments, %d exact re-tests, %d clipped, differing cells %d of %d"
+          % (dx, dy, umbra, st["steps"], st["exact_tests"], st["n_clipped"], ndiff, np.count_nonzero(ref)))
+    assert ndiff == 0
+
+
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CAPTURES)
 def test_traces_vs_reference(eng, golden, name):

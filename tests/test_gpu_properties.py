@@ -166,7 +166,7 @@ def test_c5_fine_grid_long_duration(eng):
     spec, par = workload("c5", 32, 1000)
     dp = eng.upload(spec, par)
     geom, st0 = lattice_for(eng, spec, dp)
-    assert 2000 < max(geom.nrows, geom.ncols) < 16384, (geom.nrows, geom.ncols)
+    assert 1024 < max(geom.nrows, geom.ncols) < 16384, (geom.nrows, geom.ncols)
     counts = eng.new_counts(geom)
     eng.reset_stats()
     eng.capture(spec, dp, geom, counts)
