@@ -283,9 +283,11 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
     //   right end: t_r = (v + k)/sy;  t_r < 0 -> sqrt(u^2 - v^2) (cap a);  t_r > 1 -> sx + sqrt(u^2 - (v-sy)^2) (cap b);
     //              else m v + c (the straight edge),   k = sign(sy) u sx/len,  m = sx/sy,  c = k m + u |sy|/len
     //   left end : the mirror image with -k, -c.
-    // Nodes farther than `delta` cells from both ends are decided by the interval alone; the (at most two)
-    // nodes next to an end are classified like any node (FP32 + band, exact FP64 inside the band).
-    // Rows within tau of tangency and segments flatter than 1:64 fall back to the node loop.
+    // A node is decided by the interval alone unless it lies within the FP32 error bound of an end:
+    //   |x_end error| <= eps L (17 |m| + 11)   on an edge,      <= 10 eps L^2 / h   on a cap of half-chord h
+    // (derivation in DESIGN.md; both are used with a 4x margin).  The at most two nodes inside those bounds are
+    // classified like any node (FP32 distance + band, exact FP64 inside the band).  Rows within tau of tangency
+    // and segments flatter than 1:64 use the node loop.
     const float rlen = rsqrtf(flen2);
     const float uy = u * fabsf(fbay) * rlen;
     const float kk = (fbay < 0.0f) ? -(u * fbax * rlen) : (u * fbax * rlen);
@@ -295,13 +297,10 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
     const float kisy = kk * isy;
     const float ylo = fminf(0.0f, fbay), yhi = fmaxf(0.0f, fbay);
     const float tau = fmaxf(1e-3f * u, 256.0f * EPS32 * Lm);
-    // bound on the error of an interval end [m]: coordinates 4 eps L, amplified by (1 + |m|) <= 65 on an edge,
-    // by 1/(2 h) with h >= sqrt(2 u tau - tau^2) on a cap
-    const float errx = EPS32 * Lm * (16.0f * 65.0f + 8.0f * Lm * rsqrtf(fmaxf(2.0f * u * tau - tau * tau, 1e-30f)));
-    const float delta = fmaxf(0.05f, 4.0f * errx * L.inv_dx32);
+    const float k_edge = 4.0f * EPS32 * Lm * fmaf(17.0f, fabsf(m), 11.0f) * L.inv_dx32;     // [cells]
+    const float k_cap = 40.0f * EPS32 * Lm * Lm * L.inv_dx32;                                // [cells * m]
     const int ncol = right - left;
-    const bool scan_ok = !all_exact && ncol >= ONEKA_SCAN_MIN_COLS && (fabsf(fbay) * 64.0f > fabsf(fbax)) &&
-                         delta < 0.45f && u > 0.0f;
+    const bool scan_ok = !all_exact && ncol >= ONEKA_SCAN_MIN_COLS && (fabsf(fbay) * 64.0f > fabsf(fbax)) && u > 0.0f;
 
     unsigned int *row = bm + (size_t)bottom * L.wpr;
     float fi = 0.0f;
@@ -315,23 +314,38 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
             const float ha = sqrt_fast(fmaf(-cay, cay, u2));
             const float wb = cay - fbay;
             const float hb = sqrt_fast(fmaf(-wb, wb, u2));
-            const float xr = (tr < 0.0f) ? ha : ((tr > 1.0f) ? fbax + hb : fmaf(m, cay, cr));
-            const float xl = (tl < 0.0f) ? -ha : ((tl > 1.0f) ? fbax - hb : fmaf(m, cay, -cr));
+            const bool ra = tr < 0.0f, rb = tr > 1.0f, la = tl < 0.0f, lb = tl > 1.0f;
+            const float xr = ra ? ha : (rb ? fbax + hb : fmaf(m, cay, cr));
+            const float xl = la ? -ha : (lb ? fbax - hb : fmaf(m, cay, -cr));
             if (xr > xl) {                                               // also false for nan
                 const float fl = (xl - base_x) * L.inv_dx32, fr = (xr - base_x) * L.inv_dx32;
                 const float rl = rintf(fl), rr = rintf(fr);
                 const float dl = fl - rl, dr = fr - rr;
                 int kl = (int)rl + (dl > 0.0f ? 1 : 0);                  // first node right of xl
                 int kr = (int)rr - (dr > 0.0f ? 0 : 1);                  // last node left of xr
-                if (fabsf(dl) < delta) { const int k = (int)rl; if (k >= 0 && k < ncol) kl = node_inside(rl, cay, i, left + k) ? k : k + 1; }
-                if (fabsf(dr) < delta) { const int k = (int)rr; if (k >= 0 && k < ncol) kr = node_inside(rr, cay, i, left + k) ? k : k - 1; }
+                // is the node nearest to an end inside that end's error bound?
+                const bool amb_l = la ? (fabsf(dl) * ha < k_cap) : (lb ? (fabsf(dl) * hb < k_cap) : (fabsf(dl) < k_edge));
+                const bool amb_r = ra ? (fabsf(dr) * ha < k_cap) : (rb ? (fabsf(dr) * hb < k_cap) : (fabsf(dr) < k_edge));
+                if (amb_l | amb_r) {                                     // rare (~1e-4 of rows)
+                    if (amb_l) { const int k = (int)rl; if (k >= 0 && k < ncol) kl = node_inside(rl, cay, i, left + k) ? k : k + 1; }
+                    if (amb_r) { const int k = (int)rr; if (k >= 0 && k < ncol) kr = node_inside(rr, cay, i, left + k) ? k : k - 1; }
+                }
                 kl = max(kl, 0);
                 kr = min(kr, ncol - 1);
                 if (kl <= kr) {
-                    const int ja = left + kl, jb = left + kr;
-                    for (int w = ja >> 5; w <= (jb >> 5); ++w) {
-                        const int lo = max(ja, w << 5), hi = min(jb, (w << 5) + 31);
-                        atomicOr(row + w, (0xffffffffu >> (31 - (hi - lo))) << (lo & 31));
+                    const int ja = left + kl, span = kr - kl;            // span + 1 nodes starting at column ja
+                    unsigned int *wp = row + (ja >> 5);
+                    const int sh = ja & 31;
+                    if (span < 32) {
+                        const unsigned int bits = 0xffffffffu >> (31 - span);
+                        atomicOr(wp, bits << sh);
+                        if (sh + span > 31) atomicOr(wp + 1, bits >> (32 - sh));
+                    } else {
+                        const int jb = left + kr;
+                        for (int w = ja >> 5; w <= (jb >> 5); ++w) {
+                            const int lo = max(ja, w << 5), hi = min(jb, (w << 5) + 31);
+                            atomicOr(row + w, (0xffffffffu >> (31 - (hi - lo))) << (lo & 31));
+                        }
                     }
                 }
                 done = true;
