@@ -139,6 +139,24 @@ int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice
                   const double *coef_dev, const double *start_xy_dev,
                   uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev);
 
+/* ---- Exact emulation of the reference's auto-expanding field ----------------------------- *
+ * The reference expands its grid to each trace's bounding box just before inserting it
+ * (ProbabilityField.rasterize, oneka/probabilityfield.py:335) and insert() clips every segment's
+ * window to the grid as it is at that moment (:298-301), so what a path marks depends on all paths
+ * before it, in (realization, path) order.  Two calls reproduce that exactly:
+ *   oneka_path_bboxes      tracking only; bbox_dev[R][P][4] = min x, max x, min y, max y of each path
+ *                          (the host turns their running union into per-path lattice windows);
+ *   oneka_capture_clipped  oneka_capture with clip_dev[R][P][4] = left, right, bottom, top (half-open
+ *                          lattice index ranges, 16-byte aligned) applied to every segment of the path. */
+int oneka_path_bboxes(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_dev, int64_t R, int32_t P,
+                      const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                      const double *coef_dev, const double *start_xy_dev, double *bbox_dev, uint8_t *status_dev);
+int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev, const int32_t *clip_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev);
+
 /* Statistics of everything enqueued since the last oneka_reset_stats.  Synchronises. */
 int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out);
 int oneka_reset_stats(oneka_ctx *ctx);

@@ -19,7 +19,8 @@ SYMBOLS = [
     "oneka_last_error", "oneka_abi_version", "oneka_create", "oneka_destroy", "oneka_set_stream",
     "oneka_set_workspace_limit", "oneka_synchronize", "oneka_launch_count", "oneka_set_profiling",
     "oneka_kernel_ms", "oneka_eval_points_host", "oneka_trace", "oneka_raster_traces", "oneka_capture",
-    "oneka_read_stats", "oneka_reset_stats", "oneka_capture_host", "oneka_fp64_probe",
+    "oneka_read_stats", "oneka_reset_stats", "oneka_capture_host", "oneka_fp64_probe", "oneka_path_bboxes",
+    "oneka_capture_clipped",
 ]
 
 
@@ -84,6 +85,10 @@ def load():
     L.oneka_raster_traces.argtypes = [_vp, C.POINTER(Lattice), C.c_int64, _vp, _vp, _vp, C.c_int64, _vp]
     L.oneka_capture.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.oneka_path_bboxes.argtypes = [_vp, C.POINTER(ModelDesc), _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _vp]
+    L.oneka_capture_clipped.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.oneka_read_stats.argtypes = [_vp, C.POINTER(Stats)]
     L.oneka_reset_stats.argtypes = [_vp]
     L.oneka_capture_host.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,

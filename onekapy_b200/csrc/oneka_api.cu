@@ -155,7 +155,7 @@ raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, 
     RasterCounters ctr = {0u, 0u};
     unsigned long long nseg = 0;
     for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
-        raster_seg(L, bm, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
+        raster_seg(L, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
         ++nseg;
     }
     atomicAdd(stats + STAT_STEPS, nseg);
@@ -577,11 +577,12 @@ int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntrace
     return ONEKA_OK;
 }
 
-int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
                   const double *well_xy_dev, int64_t R, int32_t P,
                   const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
                   const double *coef_dev, const double *start_xy_dev,
-                  uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev)
+                  uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
+                  const int32_t *clip_dev, double *path_bbox_dev)
 {
     if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
     int rc = check_model(m);
@@ -615,6 +616,8 @@ int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice
         tp.end_xy = end_xy_dev ? end_xy_dev + 2 * (size_t)r0 * P : nullptr;
         tp.nverts = nverts_dev ? nverts_dev + (size_t)r0 * P : nullptr;
         tp.status = status_dev ? status_dev + (size_t)r0 * P : nullptr;
+        tp.clip = clip_dev ? clip_dev + 4 * (size_t)r0 * P : nullptr;
+        tp.path_bbox = path_bbox_dev ? path_bbox_dev + 4 * (size_t)r0 * P : nullptr;
         if (raster) {
             rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps);
             if (rc) return rc;
@@ -626,6 +629,37 @@ int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice
         }
     }
     return ONEKA_OK;
+}
+
+int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                  const double *well_xy_dev, int64_t R, int32_t P,
+                  const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                  const double *coef_dev, const double *start_xy_dev,
+                  uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev)
+{
+    return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
+                        counts_dev, end_xy_dev, nverts_dev, status_dev, nullptr, nullptr);
+}
+
+int oneka_path_bboxes(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_dev, int64_t R, int32_t P,
+                      const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                      const double *coef_dev, const double *start_xy_dev, double *bbox_dev, uint8_t *status_dev)
+{
+    if (!bbox_dev) return fail(ONEKA_ERR_ARG, "bbox_dev is NULL");
+    return capture_impl(ctx, m, nullptr, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
+                        nullptr, nullptr, nullptr, status_dev, nullptr, bbox_dev);
+}
+
+int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev, const int32_t *clip_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev)
+{
+    if (!clip_dev || !lat || !counts_dev) return fail(ONEKA_ERR_ARG, "oneka_capture_clipped needs clip_dev, lat and counts_dev");
+    if (((uintptr_t)clip_dev & 15) != 0) return fail(ONEKA_ERR_ARG, "clip_dev must be 16-byte aligned");
+    return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
+                        counts_dev, end_xy_dev, nverts_dev, status_dev, clip_dev, nullptr);
 }
 
 int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,

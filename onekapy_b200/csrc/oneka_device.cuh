@@ -48,6 +48,8 @@ struct TrackParams {
     const double *start_xy;          // [P][2]
     // optional outputs (already offset)
     double *end_xy; int *nverts; unsigned char *status; int *attempts;
+    double *path_bbox;               // [R][P][4] min x, max x, min y, max y of each path's vertices, or null
+    const int *clip;                 // [R][P][4] per-path raster clip window (left, right, bottom, top), or null
     // oneka_trace only
     double *verts; int max_verts;
     // statistics
@@ -198,6 +200,11 @@ __device__ __forceinline__ double exact_distancesquared(double ax, double ay, do
 
 struct RasterCounters { unsigned int clipped, exact; };
 
+// insert() clips its window to the grid "as it is now" (probabilityfield.py:298-301).  On the fixed lattice that is
+// [0, ncols) x [0, nrows); the exact emulation of the auto-expanding field passes the window the reference's grid
+// had when this path was inserted (oneka_capture_clipped).
+struct ClipWin { int l, r, b, t; };
+
 // windows narrower than this use the node loop for every row (0 = scan-line rows always; measured on B200:
 // always-on is 8 % faster than node-only at 7-column windows (C3) and 33 % faster at 15 columns (C5))
 #ifndef ONEKA_SCAN_MIN_COLS
@@ -234,7 +241,7 @@ __device__ __forceinline__ double floor_div(double v, double org, double delta, 
     return f;
 }
 
-__device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__restrict__ bm,
+__device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__restrict__ bm, const ClipWin cw,
                                            double ax, double ay, double bx, double by, RasterCounters &ctr)
 {
     // ---- window, probabilityfield.py:298-301 ----
@@ -244,9 +251,9 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
     const double fr = floor_div(__dadd_rn(mxx, L.umbra), L.xmin, L.dx, L.inv_dx);
     const double fb = floor_div(__dsub_rn(mny, L.umbra), L.ymin, L.dy, L.inv_dy);
     const double ft = floor_div(__dadd_rn(mxy, L.umbra), L.ymin, L.dy, L.inv_dy);
-    const double lo_x = fmax(fl, 0.0), hi_x = fmin(fr + 1.0, (double)L.ncols);
-    const double lo_y = fmax(fb, 0.0), hi_y = fmin(ft + 1.0, (double)L.nrows);
-    if (fl < 0.0 || fb < 0.0 || fr + 1.0 > (double)L.ncols || ft + 1.0 > (double)L.nrows) ctr.clipped++;
+    const double lo_x = fmax(fl, (double)cw.l), hi_x = fmin(fr + 1.0, (double)cw.r);
+    const double lo_y = fmax(fb, (double)cw.b), hi_y = fmin(ft + 1.0, (double)cw.t);
+    if (fl < (double)cw.l || fb < (double)cw.b || fr + 1.0 > (double)cw.r || ft + 1.0 > (double)cw.t) ctr.clipped++;
     if (!(lo_x < hi_x) || !(lo_y < hi_y)) return;                        // empty window (also nan)
     const int left = (int)lo_x, right = (int)hi_x, bottom = (int)lo_y, top = (int)hi_y;
 
@@ -424,6 +431,11 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
     double bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
     RasterCounters ctr = {0u, 0u};
     double *vout = nullptr;
+    ClipWin cw = {0, L.ncols, 0, L.nrows};
+    if (MODE == 1 && tp.clip != nullptr && active) {
+        const int4 c = *reinterpret_cast<const int4 *>(tp.clip + 4 * ((size_t)r * tp.P + p));
+        cw.l = max(c.x, 0); cw.r = min(c.y, L.ncols); cw.b = max(c.z, 0); cw.t = min(c.w, L.nrows);
+    }
 
     double k1x = 0.0, k1y = 0.0;
     bool running = active;
@@ -513,7 +525,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         }
         if (MODE == 1) {
             // chronicle the accepted step (capturezone.py:120 -> probabilityfield.py:338-339), then reconverge
-            if (seg) raster_seg(L, bm, sax, say, x, y, ctr);
+            if (seg) raster_seg(L, bm, cw, sax, say, x, y, ctr);
             __syncwarp();
         }
     }
@@ -525,6 +537,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         if (tp.nverts) tp.nverts[g] = nvert;
         if (tp.status) tp.status[g] = (unsigned char)status;
         if (tp.attempts) tp.attempts[g] = nattempt;
+        if (tp.path_bbox) { double *pb = tp.path_bbox + 4 * g; pb[0] = bx0; pb[1] = bx1; pb[2] = by0; pb[3] = by1; }
     }
 
     // ---- statistics: warp-reduce, one atomic per warp per word ----

@@ -70,26 +70,32 @@ def compute_capturezone(xtarget, ytarget, rtarget, npaths, duration, pfield, umb
     """One realization: npaths backtraces from the ring around the target, chronicled into the
     caller's `pfield`, then pfield.register(weight)  (oneka/capturezone.py:51-123).
 
-    The field is expanded once to the bounding box of all npaths traces (the reference expands
-    trace by trace and clips each trace to the grid as it was then; see DESIGN.md, "auto-expanding
-    grid").  Truncated traces (AquiferError) are chronicled as far as they got and a warning is
-    logged, as the reference's bare except does (:249-250)."""
+    The reference expands the field trace by trace and clips each trace to the grid as it was at
+    that moment; that order dependence is reproduced exactly (Engine.clip_windows): a tracking pass
+    gives every path's bounding box, the field is expanded once to their union, and the fused pass
+    rasterises each path inside the window the reference's grid had when that path was inserted.
+    Truncated traces (AquiferError) are chronicled as far as they got and a warning is logged, as
+    the reference's bare except does (:249-250)."""
     mo, confined = lift_model(feval)
     eng = default_engine()
     spec, par = _spec_and_params(mo, confined, xtarget, ytarget, rtarget, npaths, duration,
                                  pfield.deltax, umbra, tol, maxstep)
+    if pfield.nrows == 0 or pfield.ncols == 0:
+        raise ValueError("compute_capturezone needs a ProbabilityField anchored on the target (stochastic.py:212)")
+    if pfield.deltax != pfield.deltay:
+        raise ValueError("the kernels take one spacing; deltax must equal deltay (stochastic.py:212 always passes spacing twice)")
     start = start_ring(xtarget, ytarget, rtarget, npaths)
     dp = eng.upload(spec, par, start)
     eng.reset_stats()
-    eng.capture(spec, dp)                                   # tracking only: bounding box
+    bb = eng.path_bboxes(spec, dp)                          # tracking only
     bbox = eng.read_stats()["bbox"]
+    base = LatticeGeom.of_field(pfield)
     pfield.expand(bbox[0], bbox[1], bbox[2], bbox[3])       # union of the per-trace expands (:335)
     geom = LatticeGeom.of_field(pfield)
-    if pfield.deltax != pfield.deltay:
-        spec.spacing = float(pfield.deltax)
+    clip = eng.clip_windows(base, geom, bb)
     counts = eng.new_counts(geom)
     eng.reset_stats()
-    eng.capture(spec, dp, geom, counts)
+    eng.capture(spec, dp, geom, counts, clip=clip)
     st = eng.read_stats()
     if st["n_not_ok"]:
         log.warning(' %d trace(s) terminated prematurely before duration.', st["n_not_ok"])

@@ -35,7 +35,7 @@ def create_deterministic_capturezone(
         target, npaths, duration,
         base, c_dist, p_dist, t_dist,
         stochastic_wells, observations,
-        spacing, umbra, confined, tol, maxstep, engine=None):
+        spacing, umbra, confined, tol, maxstep, engine=None, exact_clip=True):
     """Same signature and return value as oneka/deterministic.py:65-70 (+ optional engine)."""
     xtarget, ytarget, rtarget = stochastic_wells[target][0:3]
     par, mo = mean_realization(base, c_dist, p_dist, t_dist, stochastic_wells, observations, xtarget, ytarget)
@@ -46,5 +46,5 @@ def create_deterministic_capturezone(
                     duration=float(duration), base=float(base), spacing=float(spacing), umbra=float(umbra),
                     confined=bool(confined), tol=float(tol), maxstep=float(maxstep))
     eng = engine if engine is not None else default_engine()
-    res = eng.run(spec, par)
+    res = eng.run_exact(spec, par) if exact_clip else eng.run(spec, par)
     return ProbabilityField.from_counts(res["geom"], res["counts"], res["total_weight"])

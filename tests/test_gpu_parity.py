@@ -332,13 +332,30 @@ def test_run_vs_auto_expanding_reference(eng, golden, name):
     assert frac < 2e-2
 
 
+@pytest.mark.parametrize("name", CAPTURES)
+def test_run_exact_equals_auto_expanding_reference(eng, golden, name):
+    """Engine.run_exact reproduces the reference's order-dependent clipping: the grid of the executed reference,
+    left auto-expanding, cell for cell."""
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    res = eng.run_exact(spec, par)
+    ref = geom(g, "auto_")
+    gm = res["geom"]
+    assert (gm.xmin, gm.xmax, gm.ymin, gm.ymax, gm.nrows, gm.ncols) == (ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"])
+    want = g["auto_counts"].astype(np.uint32)
+    ndiff = np.count_nonzero(res["counts"] != want)
+    print("%s: exact-clip differing cells %d of %d nonzero" % (name, ndiff, np.count_nonzero(want)))
+    assert ndiff == 0 and res["total_weight"] == ref["total_weight"]
+
+
 def test_run_with_subsampled_pilot(eng, golden):
     """pilot < R: the lattice comes from a subsample + margin; result must not depend on it."""
     g = golden("sto_basic.npz")
     s, spec, par = spec_of(g)
     a = eng.run(spec, par)
-    b = eng.run(spec, par, pilot=2, margin=0.0)      # margin 0 forces the grow-and-repeat branch
-    c = eng.run(spec, par, pilot=3, margin=0.5)
+    b = eng.run(spec, par, pilot=2, margin=0.0, pilot_paths=2)      # margin 0 forces the grow-and-repeat branch
+    c = eng.run(spec, par, pilot=3, margin=2.0)
+    assert b["work_geom"] != a["work_geom"] and c["work_geom"] != a["work_geom"]
     for r in (b, c):
         assert r["geom"] == a["geom"] and np.array_equal(r["counts"], a["counts"])
 
@@ -366,7 +383,11 @@ def test_dropin_api(eng, golden):
         ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"], 1.0)
     want = g["auto_counts"].astype(float)
     assert pf.pgrid.dtype == np.float64 and pf.rgrid.dtype == bool and not pf.rgrid.any()
-    assert np.all(pf.pgrid >= want) and np.count_nonzero(pf.pgrid != want) / np.count_nonzero(want) < 2e-3
+    assert np.array_equal(pf.pgrid, want)                 # exact_clip=True (default): the reference's grid, cell for cell
+    pf_fast = det.create_deterministic_capturezone(pb["target"], 16, pb["duration"], pb["base"], pb["c_dist"], pb["p_dist"],
+                                                   pb["t_dist"], pb["wells"], obs, pb["spacing"], pb["umbra"], pb["confined"],
+                                                   pb["tol"], pb["maxstep"], exact_clip=False)
+    assert np.all(pf_fast.pgrid >= want) and np.count_nonzero(pf_fast.pgrid != want) / np.count_nonzero(want) < 2e-3
 
     # compute_capturezone with a closure of the reference's shape (stochastic.py:253-256) on a caller-owned field
     wells = [[w[0], w[1], w[2], q] for w, q in zip(pb["wells"], g["q"][0])]

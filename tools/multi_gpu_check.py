@@ -57,6 +57,14 @@ def main():
         assert res["total_weight"] == 6.0 and np.all(res["counts"] >= want)
         print("[multi-gpu] golden sto_basic over %d ranks: geometry identical, differing cells %d of %d"
               % (world, np.count_nonzero(res["counts"] != want), np.count_nonzero(want)), flush=True)
+    # (3) exact emulation of the auto-expanding grid across ranks: rank k's paths come after rank k-1's
+    res = eng.run_exact(spec, par, group=group)
+    if rank == 0:
+        gm = res["geom"]
+        assert [gm.xmin, gm.xmax, gm.ymin, gm.ymax, gm.nrows, gm.ncols] == list(ref[[0, 1, 2, 3, 6, 7]])
+        nd = np.count_nonzero(res["counts"] != want)
+        print("[multi-gpu] run_exact over %d ranks: differing cells %d of %d" % (world, nd, np.count_nonzero(want)), flush=True)
+        assert nd == 0 and res["total_weight"] == 6.0
     if group is not None:
         dist.barrier()
         dist.destroy_process_group()
