@@ -171,6 +171,20 @@ int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_la
                        uint32_t *counts_host, double *end_xy_host, int32_t *nverts_host, uint8_t *status_host,
                        oneka_stats *stats_out);
 
+/* ---- Post-processing of the count grid (the step right after the path) -------------------- *
+ * oneka_count_histogram: hist_dev[c] = number of lattice nodes whose count is c, 0 <= c < nbins
+ *   (counts >= nbins land in the last bin).  With weight-1 realizations pgrid is integer valued, so
+ *   this histogram IS the sorted exceedance curve of create_impact_plot (oneka/visualize.py:382-386:
+ *   pr = flip(sort(pgrid/total_weight)), area = (arange(n)+1)*spacing^2) and, through hist[0], the
+ *   deterministic capture-zone area (oneka/visualize.py:316-331).
+ * oneka_gaussian_smooth: out_dev[nrows][ncols] = scipy.ndimage.gaussian_filter(counts/total_weight,
+ *   sigma, mode='constant', cval=0) as used by create_probability_plot (oneka/visualize.py:228-233):
+ *   separable, axis 0 then axis 1, taps w_host[2*lw+1] (normalised, lw = int(4 sigma + 0.5)), FP64.
+ *   tmp_dev is a caller-provided scratch grid of the same size as out_dev.                       */
+int oneka_count_histogram(oneka_ctx *ctx, const uint32_t *counts_dev, int64_t ncell, int32_t nbins, uint64_t *hist_dev);
+int oneka_gaussian_smooth(oneka_ctx *ctx, const uint32_t *counts_dev, int32_t nrows, int32_t ncols, double total_weight,
+                          const double *w_host, int32_t lw, double *tmp_dev, double *out_dev);
+
 /* ---- FP64 pipe probe ------------------------------------------------------------------ *
  * Times a register-resident DFMA kernel (no memory traffic) and reports the achieved
  * FP64 rate; bench.py uses it as the measured FP64 roofline denominator.  Synchronous.  */

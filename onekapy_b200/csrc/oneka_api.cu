@@ -215,6 +215,43 @@ fp64_probe_kernel(int iters, double seed, double *sink)
     if (s == 12345.678) sink[0] = s;     // never true; keeps the chains alive
 }
 
+// exceedance histogram of the count grid (visualize.py:382-386 is a sort of integer-valued data)
+__global__ void __launch_bounds__(256)
+count_histogram_kernel(const unsigned int *counts, long long ncell, int nbins, unsigned long long *hist)
+{
+    unsigned long long zeros = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned int c = counts[i];
+        if (c == 0) { ++zeros; continue; }                          // most nodes: aggregate per warp below
+        atomicAdd(hist + min(c, (unsigned int)(nbins - 1)), 1ULL);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_down_sync(0xffffffffu, zeros, o);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(hist, zeros);
+}
+
+// one axis of scipy.ndimage.gaussian_filter(mode='constant', cval=0): out = sum_k w[k] in[.. + k - lw ..]
+//   AXIS 0: along rows (y), AXIS 1: along columns (x).  FROM_COUNTS: input is counts * scale.
+template <int AXIS, bool FROM_COUNTS>
+__global__ void __launch_bounds__(256)
+gaussian_axis_kernel(const unsigned int *counts, const double *in, double scale, int nrows, int ncols,
+                     const double *__restrict__ w, int lw, double *out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= ncols) return;
+    double acc = 0.0;
+    for (int k = -lw; k <= lw; ++k) {
+        const int ii = AXIS == 0 ? i + k : i;
+        const int jj = AXIS == 0 ? j : j + k;
+        if (ii < 0 || ii >= nrows || jj < 0 || jj >= ncols) continue;   // cval = 0
+        const size_t idx = (size_t)ii * ncols + jj;
+        const double v = FROM_COUNTS ? (double)counts[idx] * scale : in[idx];
+        acc = fma(w[k + lw], v, acc);
+    }
+    out[(size_t)i * ncols + j] = acc;
+}
+
 // ------------------------------------------------------------------------------------------
 // Host helpers
 // ------------------------------------------------------------------------------------------
@@ -721,6 +758,44 @@ int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_la
     if (status_host && RP) CUDA_TRY(cudaMemcpyAsync(status_host, base + o_stt, RP, cudaMemcpyDeviceToHost, s));
     if (stats_out) return oneka_read_stats(ctx, stats_out);
     CUDA_TRY(cudaStreamSynchronize(s));
+    return ONEKA_OK;
+}
+
+int oneka_count_histogram(oneka_ctx *ctx, const uint32_t *counts_dev, int64_t ncell, int32_t nbins, uint64_t *hist_dev)
+{
+    if (!ctx || !counts_dev || !hist_dev || ncell < 0 || nbins < 2) return fail(ONEKA_ERR_ARG, "bad argument to oneka_count_histogram");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(hist_dev, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
+    if (ncell == 0) return ONEKA_OK;
+    long long blocks = (ncell + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    count_histogram_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(counts_dev, ncell, nbins, (unsigned long long *)hist_dev);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ONEKA_OK;
+}
+
+int oneka_gaussian_smooth(oneka_ctx *ctx, const uint32_t *counts_dev, int32_t nrows, int32_t ncols, double total_weight,
+                          const double *w_host, int32_t lw, double *tmp_dev, double *out_dev)
+{
+    if (!ctx || !counts_dev || !w_host || !tmp_dev || !out_dev || nrows <= 0 || ncols <= 0 || lw < 0 || !(total_weight > 0.0))
+        return fail(ONEKA_ERR_ARG, "bad argument to oneka_gaussian_smooth");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double *w_dev = nullptr;
+    const size_t wb = (size_t)(2 * lw + 1) * sizeof(double);
+    CUDA_TRY(cudaMalloc(&w_dev, wb));
+    cudaError_t e = cudaMemcpyAsync(w_dev, w_host, wb, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const dim3 grid((ncols + 255) / 256, nrows);
+        gaussian_axis_kernel<0, true><<<grid, 256, 0, ctx->stream>>>(counts_dev, nullptr, 1.0 / total_weight, nrows, ncols, w_dev, lw, tmp_dev);
+        gaussian_axis_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(nullptr, tmp_dev, 1.0, nrows, ncols, w_dev, lw, out_dev);
+        ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    cudaStreamSynchronize(ctx->stream);      // w_host / w_dev lifetime
+    cudaFree(w_dev);
+    if (e != cudaSuccess) return fail(ONEKA_ERR_CUDA, "gaussian smooth failed: %s", cudaGetErrorString(e));
     return ONEKA_OK;
 }
 
