@@ -97,15 +97,17 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
 {
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
+    __shared__ double s_lat[5];
     double2 *s_wxy = s_dyn;
     double *s_w = reinterpret_cast<double *>(s_dyn + tp.nw);
+    if (MODE == 1) stage_lattice(L, s_lat);
 
     const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long r = blockIdx.x / chunks;
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
     stage_realization<CONFINED>(tp, r, rc, s_wxy, s_w);
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE>(tp, L, bm, rc, s_wxy, s_w, r, p, p < tp.P);
+    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wxy, s_w, r, p, p < tp.P);
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per
@@ -147,6 +149,9 @@ __global__ void __launch_bounds__(128)
 raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, const double *verts,
                      const int *real_of, long long s0, long long s1, unsigned int *bitmaps, unsigned long long *stats)
 {
+    __shared__ double s_lat[5];
+    stage_lattice(L, s_lat);
+    __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntraces) return;
     const long long r = real_of[t];
@@ -155,7 +160,7 @@ raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, 
     RasterCounters ctr = {0u, 0u};
     unsigned long long nseg = 0;
     for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
-        raster_seg(L, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
+        raster_seg(L, s_lat, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
         ++nseg;
     }
     atomicAdd(stats + STAT_STEPS, nseg);

@@ -219,12 +219,19 @@ __device__ __forceinline__ float sqrt_fast(float a)
     return r;
 }
 
-__device__ __noinline__ bool exact_cell_test(double xmin, double ymin, double dx, double dy, double umbra2,
-                                             double ax, double ay, double bx, double by, int i, int j)
+// Cold path.  `lat` = {xmin, ymin, dx, dy, umbra^2} in SHARED memory: were these taken from the kernel parameters,
+// ptxas hoists the ten constant-bank loads of the argument set-up out of the rare branch and into every row
+// (measured: 12 of ~60 instructions per row).
+__device__ __noinline__ bool exact_cell_test(const double *lat, double ax, double ay, double bx, double by, int i, int j)
 {
-    const double cx = __dadd_rn(xmin, __dmul_rn((double)j, dx));         // probabilityfield.py:306
-    const double cy = __dadd_rn(ymin, __dmul_rn((double)i, dy));         // probabilityfield.py:307
-    return exact_distancesquared(ax, ay, bx, by, cx, cy) < umbra2;       // :309 (nan -> false)
+    const double cx = __dadd_rn(lat[0], __dmul_rn((double)j, lat[2]));   // probabilityfield.py:306
+    const double cy = __dadd_rn(lat[1], __dmul_rn((double)i, lat[3]));   // probabilityfield.py:307
+    return exact_distancesquared(ax, ay, bx, by, cx, cy) < lat[4];       // :309 (nan -> false)
+}
+
+__device__ __forceinline__ void stage_lattice(const LatticeDev &L, double *s_lat)
+{
+    if (threadIdx.x == 0) { s_lat[0] = L.xmin; s_lat[1] = L.ymin; s_lat[2] = L.dx; s_lat[3] = L.dy; s_lat[4] = L.umbra2; }
 }
 
 // floor((v - org) / delta) with the reference's two IEEE operations (sub, div).  The quotient is
@@ -241,8 +248,8 @@ __device__ __forceinline__ double floor_div(double v, double org, double delta, 
     return f;
 }
 
-__device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__restrict__ bm, const ClipWin cw,
-                                           double ax, double ay, double bx, double by, RasterCounters &ctr)
+__device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_lat, unsigned int *__restrict__ bm,
+                                           const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr)
 {
     // ---- window, probabilityfield.py:298-301 ----
     const double mnx = (bx < ax) ? bx : ax, mxx = (bx > ax) ? bx : ax;
@@ -282,7 +289,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
         const float d2 = fmaf(px, px, py * py);
         if (fabsf(d2 - u2) > E) return d2 < u2;
         ctr.exact++;
-        return exact_cell_test(L.xmin, L.ymin, L.dx, L.dy, L.umbra2, ax, ay, bx, by, i, j);
+        return exact_cell_test(s_lat, ax, ay, bx, by, i, j);
     };
 
     // ---- scan-line constants (see "Scan-line rows" in DESIGN.md) ----
@@ -379,7 +386,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, unsigned int *__
                 do {
                     const int k = __ffs(amb) - 1;
                     amb &= amb - 1;
-                    if (exact_cell_test(L.xmin, L.ymin, L.dx, L.dy, L.umbra2, ax, ay, bx, by, i, jc + k)) mask |= 1u << k;
+                    if (exact_cell_test(s_lat, ax, ay, bx, by, i, jc + k)) mask |= 1u << k;
                     else mask &= ~(1u << k);
                 } while (amb);
             }
@@ -405,7 +412,7 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
 template <bool CONFINED, int MODE>
-__device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, unsigned int *bm,
+__device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double2 *s_wxy, const double *s_w,
                                             long long r, int p, bool active)
 {
@@ -525,7 +532,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         }
         if (MODE == 1) {
             // chronicle the accepted step (capturezone.py:120 -> probabilityfield.py:338-339), then reconverge
-            if (seg) raster_seg(L, bm, cw, sax, say, x, y, ctr);
+            if (seg) raster_seg(L, s_lat, bm, cw, sax, say, x, y, ctr);
             __syncwarp();
         }
     }
