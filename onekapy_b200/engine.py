@@ -301,40 +301,9 @@ class Engine:
         return bb
 
     def clip_windows(self, base: LatticeGeom, final: LatticeGeom, bb, prior=None):
-        """Per-path raster windows of the reference's auto-expanding grid, as lattice index ranges of `final`.
-
-        `base` is the grid before the first path (3 x 3 on the target for a fresh field); path n is inserted
-        after the grid has been expanded to the union of the bounding boxes of paths 0..n (rasterize(),
-        probabilityfield.py:335, in (realization, path) order) -- a running min/max (torch.cummin/cummax on
-        the device).  expand() moves xmin down by whole cells until it is strictly below the box (:229-245):
-        k = floor((xmin0 - c)/delta) + 1 cells when c <= xmin0.  `prior` = box of everything inserted earlier
-        (other ranks' shards).  Returns int32 [R, P, 4] = left, right, bottom, top (half-open)."""
-        torch = self.torch
-        R, P = int(bb.shape[0]), int(bb.shape[1])
-        f = bb.reshape(-1, 4)
-        lo_x = torch.cummin(f[:, 0], 0).values
-        hi_x = torch.cummax(f[:, 1], 0).values
-        lo_y = torch.cummin(f[:, 2], 0).values
-        hi_y = torch.cummax(f[:, 3], 0).values
-        if prior is not None and np.all(np.isfinite(prior)):
-            lo_x = torch.clamp(lo_x, max=float(prior[0]))
-            hi_x = torch.clamp(hi_x, min=float(prior[1]))
-            lo_y = torch.clamp(lo_y, max=float(prior[2]))
-            hi_y = torch.clamp(hi_y, min=float(prior[3]))
-        i0, j0 = final.offset_of(base)                       # where the base grid sits inside the final lattice
-
-        def cells_below(g0, c, d):                            # expansions so that g0 - k d < c
-            return torch.where(c <= g0, torch.floor((g0 - c) / d) + 1.0, torch.zeros_like(c))
-
-        def cells_above(g1, c, d):                            # expansions so that g1 + k d > c
-            return torch.where(c >= g1, torch.floor((c - g1) / d) + 1.0, torch.zeros_like(c))
-
-        left = j0 - cells_below(base.xmin, lo_x, base.deltax)
-        right = j0 + base.ncols + cells_above(base.xmax, hi_x, base.deltax)
-        bottom = i0 - cells_below(base.ymin, lo_y, base.deltay)
-        top = i0 + base.nrows + cells_above(base.ymax, hi_y, base.deltay)
-        clip = torch.stack([left, right, bottom, top], dim=1).to(torch.int32).reshape(R, P, 4).contiguous()
-        return clip
+        """Per-path raster windows of the reference's auto-expanding grid (see lattice.clip_windows)."""
+        from .lattice import clip_windows
+        return clip_windows(self.torch, base, final, bb, prior)
 
     def run_exact(self, spec: FlowSpec, params: RealizationParams, group=None, per_path=False, base: Optional[LatticeGeom] = None):
         """Like run(), but reproduces the reference's order-dependent clipping exactly: a tracking pass

@@ -87,3 +87,41 @@ def final_geometry(deltax, deltay, xo, yo, bbox):
     """The extents the reference's auto-expanding field ends with when the union of all trace
     bounding boxes is `bbox` (successive expansions commute with one expansion to the union)."""
     return LatticeGeom.anchored(deltax, deltay, xo, yo).expanded(*bbox)
+
+
+def clip_windows(torch, base, final, bb, prior=None):
+    """Per-path raster windows of the reference's auto-expanding grid, as lattice index ranges of `final`.
+
+    `base` is the grid before the first path (3 x 3 on the target for a fresh field); path n is inserted
+    after the grid has been expanded to the union of the bounding boxes of paths 0..n (rasterize(),
+    probabilityfield.py:335, in (realization, path) order) -- a running min/max (torch.cummin/cummax, on
+    whatever device `bb` lives).  expand() moves xmin down by whole cells until it is strictly below the
+    box (:229-245): k = floor((xmin0 - c)/delta) + 1 cells when c <= xmin0, else 0; likewise upwards.
+    `prior` = box of everything inserted earlier (other ranks' shards).
+    bb: float64 tensor [R, P, 4] = min x, max x, min y, max y.  Returns int32 [R, P, 4] = left, right,
+    bottom, top (half-open)."""
+    import math
+    R, P = int(bb.shape[0]), int(bb.shape[1])
+    f = bb.reshape(-1, 4)
+    lo_x = torch.cummin(f[:, 0], 0).values
+    hi_x = torch.cummax(f[:, 1], 0).values
+    lo_y = torch.cummin(f[:, 2], 0).values
+    hi_y = torch.cummax(f[:, 3], 0).values
+    if prior is not None and all(math.isfinite(v) for v in prior):
+        lo_x = torch.clamp(lo_x, max=float(prior[0]))
+        hi_x = torch.clamp(hi_x, min=float(prior[1]))
+        lo_y = torch.clamp(lo_y, max=float(prior[2]))
+        hi_y = torch.clamp(hi_y, min=float(prior[3]))
+    i0, j0 = final.offset_of(base)                       # where the base grid sits inside the final lattice
+
+    def cells_below(g0, c, d):                            # expansions so that g0 - k d < c
+        return torch.where(c <= g0, torch.floor((g0 - c) / d) + 1.0, torch.zeros_like(c))
+
+    def cells_above(g1, c, d):                            # expansions so that g1 + k d > c
+        return torch.where(c >= g1, torch.floor((c - g1) / d) + 1.0, torch.zeros_like(c))
+
+    left = j0 - cells_below(base.xmin, lo_x, base.deltax)
+    right = j0 + base.ncols + cells_above(base.xmax, hi_x, base.deltax)
+    bottom = i0 - cells_below(base.ymin, lo_y, base.deltay)
+    top = i0 + base.nrows + cells_above(base.ymax, hi_y, base.deltay)
+    return torch.stack([left, right, bottom, top], dim=1).to(torch.int32).reshape(R, P, 4).contiguous()

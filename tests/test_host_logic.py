@@ -177,3 +177,30 @@ def test_final_geometry_equals_sequential_expansion(golden):
         assert [big.xmin, big.xmax, big.ymin, big.ymax, big.nrows, big.ncols] == list(fx[[0, 1, 2, 3, 6, 7]])
         i0, j0 = big.offset_of(fg)
         assert big.xmin + j0 * s["spacing"] == fg.xmin and big.ymin + i0 * s["spacing"] == fg.ymin
+
+
+def test_clip_windows_replay_reference_expansion(golden):
+    """lattice.clip_windows (closed form + running union) == replaying expand() trace by trace, which is what
+    the reference does (probabilityfield.py:335) -- checked on the executed reference's own traces."""
+    import torch
+    from helpers import traces_of
+    from onekapy_b200.lattice import clip_windows
+    for name in ["sto_basic.npz", "sto_perham.npz", "fwd_basic.npz", "det_basic.npz"]:
+        g = golden(name)
+        s = scal(g)
+        tr = traces_of(g)
+        bb = np.array([[t[:, 0].min(), t[:, 0].max(), t[:, 1].min(), t[:, 1].max()] for t in tr])
+        R = len(g["k"])
+        base = LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"])
+        final = base.expanded(bb[:, 0].min(), bb[:, 1].max(), bb[:, 2].min(), bb[:, 3].max())
+        got = clip_windows(torch, base, final, torch.from_numpy(bb).reshape(R, s["P"], 4)).reshape(-1, 4).numpy()
+        pf = ProbabilityField(s["spacing"], s["spacing"], s["xt"], s["yt"])
+        for n, b in enumerate(bb):
+            pf.expand(*b)
+            i0, j0 = final.offset_of(LatticeGeom.of_field(pf))
+            assert list(got[n]) == [j0, j0 + pf.ncols, i0, i0 + pf.nrows], (name, n)
+        assert (pf.nrows, pf.ncols) == (final.nrows, final.ncols)
+        # a prior box (earlier ranks) only ever widens the windows
+        prior = (bb[:, 0].min() + 50, bb[:, 1].max() - 50, bb[:, 2].min() + 50, bb[:, 3].max() - 50)
+        wide = clip_windows(torch, base, final, torch.from_numpy(bb).reshape(R, s["P"], 4), prior).reshape(-1, 4).numpy()
+        assert np.all(wide[:, 0] <= got[:, 0]) and np.all(wide[:, 1] >= got[:, 1])
