@@ -292,8 +292,12 @@ def run_ours(args):
     att_per_launch = stats["attempts"] / max(1, kms["track_launches"])
     achieved = att_per_launch * flops_per_attempt(nw) / (track_ms * 1e-3) / 1e12
     nominal = 148 * 64 * 2 * (sampler.max_mhz or 1965) * 1e6 / 1e12
+    # DRAM traffic of the fused kernel from the ncu --set full capture in profiles/ (27.9 MB per 1000 realizations of
+    # the perham field, dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch: the path is not HBM-bound
+    traffic = 27.9e6 * (R / 1000.0) if args.workload == "c3" else None
     roofline = {"bound": "fp64", "kernel": "track_kernel<confined, raster>", "achieved": achieved, "peak": probe_tf,
-                "unit": "TFLOP/s", "frac": achieved / probe_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / probe_tf, "traffic": traffic,
+                "traffic_note": "bytes per launch scaled from profiles/r01_track_kernel_raw.csv (ncu --set full at R=1000); HBM is idle (0.01 % of peak), the bound is the FP64 pipe",
                 "peak_source": "in-run DFMA probe (oneka_fp64_probe); MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x max clock = %.1f" % nominal,
                 "flops_per_attempt": flops_per_attempt(nw), "attempts_per_launch": att_per_launch, "kernel_ms_per_launch": track_ms,
                 "flush_kernel_ms_per_step": kms["flush_ms"] / args.steps,

@@ -33,12 +33,15 @@ static int fail(int code, const char *fmt, ...)
             return fail(ONEKA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int TRACK_THREADS = 128;          // 4 warps per CTA; every warp stays inside one realization
+#ifndef ONEKA_TRACK_THREADS
+#define ONEKA_TRACK_THREADS 128
+#endif
+constexpr int TRACK_THREADS = ONEKA_TRACK_THREADS;   // warps per CTA x 32; every warp stays inside one realization
 #ifndef TRACK_MIN_CTAS
-#define TRACK_MIN_CTAS 6                    // tracking only: <= 80 registers/thread -> 24 warps per SM
+#define TRACK_MIN_CTAS (768 / ONEKA_TRACK_THREADS)   // tracking only: <= 80 registers/thread -> 24 warps per SM
 #endif
 #ifndef FUSED_MIN_CTAS
-#define FUSED_MIN_CTAS 6                    // + rasteriser: 80 registers too (260 B of spills, all on the cold exact/fallback
+#define FUSED_MIN_CTAS (768 / ONEKA_TRACK_THREADS)                    // + rasteriser: 80 registers too (260 B of spills, all on the cold exact/fallback
 #endif                                      // paths); measured 6.19e9 attempts/s vs 5.92e9 at 4 CTAs/120 regs, 5.74e9 at 5/96
 constexpr int N_STATS = 16;
 
@@ -305,7 +308,9 @@ static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_d
     return tp;
 }
 
-static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double)); }
+// + 32 B: ptxas widens the scaled-discharge loads of the remainder iterations to LDS.128 (w[i], w[i+1]); with an odd
+// number of wells the second half lies 8 bytes past w[nw-1].  Harmless on hardware, but compute-sanitizer flags it.
+static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double)) + 32; }
 
 static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
 {
@@ -555,7 +560,7 @@ int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const doub
         if (!(mm.tol > 0)) mm.tol = 1.0;
         if (!(mm.maxstep > 0)) mm.maxstep = 1.0;
         TrackParams tp = make_track(&mm, d_wxy, 1, 1, d_q, d_k, d_n, d_H, d_cf, nullptr, ctx->stats_dev);
-        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * sizeof(double));
+        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * sizeof(double)) + 32;
         if (smem > 48 * 1024) TRY2(cudaFuncSetAttribute(eval_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_points_kernel<<<1, 128, smem, s>>>(tp, npts, d_pts, d_out);
         ctx->launches++;
