@@ -159,14 +159,16 @@ def cpu_geom(spec, params):
 
 def cpu_sample(spec, params, geom, target_s=12.0):
     """Bounded CPU sample: calibrate on one realization per thread, then size the sample for ~target_s."""
-    from oracle import oracle as O
-    cores = O.num_threads()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     n0 = min(len(params), cores)
-    t, att, stp = oracle_run(spec, params.slice(0, n0), geom)
+    t, att, stp = oracle_run(spec, params.slice(0, n0), geom, nthreads=cores)
     per = t / max(1, n0) * cores                       # seconds of one thread per realization
     n = int(min(len(params), max(n0, cores * max(1, int(target_s / max(per, 1e-9))))))
     if n > n0:
-        t, att, stp = oracle_run(spec, params.slice(0, n), geom)
+        t, att, stp = oracle_run(spec, params.slice(0, n), geom, nthreads=cores)
     else:
         n = n0
     return dict(seconds=t, realizations=n, attempts=att, steps=stp, cores=cores)
@@ -181,18 +183,23 @@ def run_reference_arm(args):
     O.build()
     spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed)
     geom = cpu_geom(spec, params)
-    cores = O.num_threads()
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the
+    # reference arm on one core at N > 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     # calibrate the per-step sample so that warmup + steps finish in ~2 minutes
-    t1, a1, _ = oracle_run(spec, params.slice(0, min(len(params), cores)), geom)
+    t1, a1, _ = oracle_run(spec, params.slice(0, min(len(params), cores)), geom, nthreads=cores)
     per_real = t1 / min(len(params), cores)
     budget = 100.0 / max(1, args.steps + args.warmup)
     n = int(min(len(params), max(cores, int(budget / max(per_real, 1e-9)))))
     sub = params.slice(0, n)
     for _ in range(args.warmup):
-        oracle_run(spec, sub, geom)
+        oracle_run(spec, sub, geom, nthreads=cores)
     tot_t, tot_a = 0.0, 0
     for _ in range(args.steps):
-        t, a, _ = oracle_run(spec, sub, geom)
+        t, a, _ = oracle_run(spec, sub, geom, nthreads=cores)
         tot_t += t
         tot_a += a
     value = tot_a / tot_t

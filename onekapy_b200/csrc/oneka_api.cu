@@ -692,6 +692,7 @@ int oneka_path_bboxes(oneka_ctx *ctx, const oneka_model_desc *m, const double *w
                       const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
                       const double *coef_dev, const double *start_xy_dev, double *bbox_dev, uint8_t *status_dev)
 {
+    if (R == 0) return ONEKA_OK;
     if (!bbox_dev) return fail(ONEKA_ERR_ARG, "bbox_dev is NULL");
     return capture_impl(ctx, m, nullptr, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
                         nullptr, nullptr, nullptr, status_dev, nullptr, bbox_dev);
@@ -703,6 +704,7 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
                           const double *coef_dev, const double *start_xy_dev, const int32_t *clip_dev,
                           uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev)
 {
+    if (R == 0) return ONEKA_OK;
     if (!clip_dev || !lat || !counts_dev) return fail(ONEKA_ERR_ARG, "oneka_capture_clipped needs clip_dev, lat and counts_dev");
     if (((uintptr_t)clip_dev & 15) != 0) return fail(ONEKA_ERR_ARG, "clip_dev must be 16-byte aligned");
     return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,

@@ -333,16 +333,21 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
             const float xl = la ? -ha : (lb ? fbax - hb : fmaf(m, cay, -cr));
             if (xr > xl) {                                               // also false for nan
                 const float fl = (xl - base_x) * L.inv_dx32, fr = (xr - base_x) * L.inv_dx32;
-                const float rl = rintf(fl), rr = rintf(fr);
+                // round-to-nearest and float->int through the 1.5 * 2^23 trick (FMA-pipe adds instead of the
+                // quarter-rate FRND / F2I of the XU pipe); exact for |f| < 2^22, the window is far smaller
+                constexpr float MAGIC = 12582912.0f;
+                const float tl_m = fl + MAGIC, tr_m = fr + MAGIC;
+                const float rl = tl_m - MAGIC, rr = tr_m - MAGIC;
+                const int il = __float_as_int(tl_m) - 0x4B400000, ir = __float_as_int(tr_m) - 0x4B400000;
                 const float dl = fl - rl, dr = fr - rr;
-                int kl = (int)rl + (dl > 0.0f ? 1 : 0);                  // first node right of xl
-                int kr = (int)rr - (dr > 0.0f ? 0 : 1);                  // last node left of xr
+                int kl = il + (dl > 0.0f ? 1 : 0);                       // first node right of xl
+                int kr = ir - (dr > 0.0f ? 0 : 1);                       // last node left of xr
                 // is the node nearest to an end inside that end's error bound?
                 const bool amb_l = la ? (fabsf(dl) * ha < k_cap) : (lb ? (fabsf(dl) * hb < k_cap) : (fabsf(dl) < k_edge));
                 const bool amb_r = ra ? (fabsf(dr) * ha < k_cap) : (rb ? (fabsf(dr) * hb < k_cap) : (fabsf(dr) < k_edge));
                 if (amb_l | amb_r) {                                     // rare (~1e-4 of rows)
-                    if (amb_l) { const int k = (int)rl; if (k >= 0 && k < ncol) kl = node_inside(rl, cay, i, left + k) ? k : k + 1; }
-                    if (amb_r) { const int k = (int)rr; if (k >= 0 && k < ncol) kr = node_inside(rr, cay, i, left + k) ? k : k - 1; }
+                    if (amb_l) { const int k = il; if (k >= 0 && k < ncol) kl = node_inside(rl, cay, i, left + k) ? k : k + 1; }
+                    if (amb_r) { const int k = ir; if (k >= 0 && k < ncol) kr = node_inside(rr, cay, i, left + k) ? k : k - 1; }
                 }
                 kl = max(kl, 0);
                 kr = min(kr, ncol - 1);

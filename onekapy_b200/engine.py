@@ -67,7 +67,9 @@ class RealizationParams:
         self.poro = np.ascontiguousarray(self.poro, dtype=np.float64).reshape(R)
         self.thick = np.ascontiguousarray(self.thick, dtype=np.float64).reshape(R)
         self.coef = np.ascontiguousarray(self.coef, dtype=np.float64).reshape(R, 6)
-        self.q = np.ascontiguousarray(self.q, dtype=np.float64).reshape(R, -1)
+        q = np.ascontiguousarray(self.q, dtype=np.float64)
+        nw = q.shape[-1] if q.ndim == 2 else (q.size // R if R else 0)
+        self.q = q.reshape(R, nw)
 
     def __len__(self):
         return len(self.cond)
@@ -336,6 +338,8 @@ class Engine:
             true_bbox = (okall[:, 0].min(), okall[:, 1].max(), okall[:, 2].min(), okall[:, 3].max())
         else:
             true_bbox = mine
+        if parallel.sum_int(R, group, self.device if group is not None else None) == 0:
+            return self._empty_result(spec, base)
         if not np.all(np.isfinite(true_bbox)):
             raise OnekaError("non-finite bounding box %r" % (true_bbox,))
         final = base.expanded(*true_bbox)
@@ -384,6 +388,12 @@ class Engine:
         pp = dict(end_xy=end_xy, nverts=nverts, status=status) if per_path else None
         return counts, st.as_dict(), pp
 
+    def _empty_result(self, spec, base=None):
+        g = base if base is not None else LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget)
+        z = dict(attempts=0, steps=0, paths=0, n_not_ok=0, n_clipped=0, exact_tests=0, bbox=(np.inf, -np.inf, np.inf, -np.inf))
+        return dict(counts=np.zeros((g.nrows, g.ncols), dtype=np.uint32), geom=g, total_weight=0.0, stats=z, per_path=None,
+                    work_geom=g)
+
     # -- the public flow -----------------------------------------------------------------------
     def run(self, spec: FlowSpec, params: RealizationParams, pilot=256, margin=0.5, group=None, per_path=False,
             pilot_paths=128):
@@ -416,6 +426,8 @@ class Engine:
             else:
                 self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
         bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, dev)
+        if parallel.sum_int(R, group, dev) == 0:
+            return self._empty_result(spec)              # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
         if not np.all(np.isfinite(bbox)):
             raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
         pad = margin

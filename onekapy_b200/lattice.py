@@ -102,6 +102,8 @@ def clip_windows(torch, base, final, bb, prior=None):
     bottom, top (half-open)."""
     import math
     R, P = int(bb.shape[0]), int(bb.shape[1])
+    if R * P == 0:
+        return torch.zeros((R, P, 4), dtype=torch.int32, device=bb.device)
     f = bb.reshape(-1, 4)
     lo_x = torch.cummin(f[:, 0], 0).values
     hi_x = torch.cummax(f[:, 1], 0).values

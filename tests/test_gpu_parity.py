@@ -430,6 +430,17 @@ def test_dropin_api(eng, golden):
     assert np.count_nonzero(pfs.pgrid != gs["auto_counts"]) / np.count_nonzero(gs["auto_counts"]) < 5e-3
 
 
+def test_zero_realizations(eng, golden):
+    """nrealizations = 0 leaves the fresh 3 x 3 field (oneka/stochastic.py:212, loop :220 does not run)."""
+    from onekapy_b200.engine import RealizationParams
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    empty = RealizationParams(q=np.zeros((0, par.q.shape[1])), cond=[], poro=[], thick=[], coef=np.zeros((0, 6)))
+    for res in (eng.run(spec, empty), eng.run_exact(spec, empty)):
+        assert res["total_weight"] == 0.0 and res["counts"].shape == (3, 3) and not res["counts"].any()
+        assert (res["geom"].xmin, res["geom"].xmax) == (s["xt"] - s["spacing"], s["xt"] + s["spacing"])
+
+
 def test_bad_arguments(eng, golden):
     from onekapy_b200.engine import OnekaError
     from onekapy_b200.lattice import LatticeGeom

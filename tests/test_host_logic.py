@@ -204,3 +204,11 @@ def test_clip_windows_replay_reference_expansion(golden):
         prior = (bb[:, 0].min() + 50, bb[:, 1].max() - 50, bb[:, 2].min() + 50, bb[:, 3].max() - 50)
         wide = clip_windows(torch, base, final, torch.from_numpy(bb).reshape(R, s["P"], 4), prior).reshape(-1, 4).numpy()
         assert np.all(wide[:, 0] <= got[:, 0]) and np.all(wide[:, 1] >= got[:, 1])
+
+
+def test_empty_realization_params():
+    from onekapy_b200.engine import RealizationParams
+    p = RealizationParams(q=np.zeros((0, 29)), cond=[], poro=[], thick=[], coef=np.zeros((0, 6)))
+    assert len(p) == 0 and p.q.shape == (0, 29) and p.coef.shape == (0, 6)
+    full = RealizationParams(q=np.ones((4, 3)), cond=np.ones(4), poro=np.ones(4), thick=np.ones(4), coef=np.ones((4, 6)))
+    assert full.slice(2, 2).q.shape == (0, 3) and full.slice(1, 4, 2).q.shape == (2, 3)

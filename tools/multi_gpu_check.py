@@ -65,6 +65,14 @@ def main():
         nd = np.count_nonzero(res["counts"] != want)
         print("[multi-gpu] run_exact over %d ranks: differing cells %d of %d" % (world, nd, np.count_nonzero(want)), flush=True)
         assert nd == 0 and res["total_weight"] == 6.0
+    # (4) fewer realizations than ranks: empty shards must take part in every collective
+    r0, r1 = parallel.shard_range(1, rank, world)
+    one = RealizationParams(q=g["q"][r0:r1], cond=g["k"][r0:r1], poro=g["n"][r0:r1], thick=g["H"][r0:r1], coef=g["coef"][r0:r1])
+    a = eng.run(spec, one, group=group)
+    b = eng.run_exact(spec, one, group=group)
+    if rank == 0:
+        assert a["total_weight"] == b["total_weight"] == 1.0 and a["counts"].max() == 1 and a["geom"] == b["geom"]
+        print("[multi-gpu] 1 realization over %d ranks (empty shards): ok, %d cells" % (world, np.count_nonzero(b["counts"])), flush=True)
     if group is not None:
         dist.barrier()
         dist.destroy_process_group()
