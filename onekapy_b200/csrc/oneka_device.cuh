@@ -112,6 +112,11 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 //   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
 //   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
 //   reference's AquiferError -> PATH_AQUIFER_DRY.
+#ifndef ONEKA_WELL_UNROLL
+#define ONEKA_WELL_UNROLL 4
+#endif
+constexpr int WELL_UNROLL = ONEKA_WELL_UNROLL;
+
 template <bool CONFINED>
 __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *__restrict__ s_wxy,
                                            const double *__restrict__ s_w, int nw,
@@ -122,7 +127,7 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
     double lsum = 0.0;
-#pragma unroll 4
+#pragma unroll WELL_UNROLL
     for (int i = 0; i < nw; ++i) {
         const double2 wxy = s_wxy[i];
         const double w = s_w[i];
