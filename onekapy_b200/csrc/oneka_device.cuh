@@ -167,19 +167,20 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
 // Rasteriser.
 //
 // insert() (probabilityfield.py:296-310) marks every lattice node of the clipped window whose
-// distancesquared() (:407-427) to the segment is < umbra^2.  Here:
-//   1. the window is computed with the reference's own IEEE operations (sub, sub, div, floor);
-//   2. each node is classified in FP32 relative to endpoint a (projection clamp form, 9 FP32
-//      ops on the otherwise idle FP32 pipe).  |d2_fp32 - d2_exact| <= 44 eps32 L^2 where
-//      L = max(|bax|,|bay|) + umbra + max(dx,dy) bounds every |cax|,|cay| in the window
-//      (derivation in DESIGN.md); the reference's own FP64 value is within 32 eps64 (..)^2 of
-//      exact, which is 2^-29 times smaller.  With band E = 128 eps32 L^2:
-//         d2_fp32 <  umbra^2 - E  -> inside  (same answer as the reference)
-//         d2_fp32 >  umbra^2 + E  -> outside (same answer as the reference)
-//         otherwise (incl. nan)   -> evaluate the reference formula in unfused FP64;
-//   3. the bits of one bitmap word are OR-ed into the realization's bitmap with one RED.OR.
-// Segments shorter than 1e-10 m (never produced by the integrator except by an exact clamp)
-// take the exact path for every node; zero-length segments set nothing (0/0 = nan in :421).
+// distancesquared() (:407-427) to the segment is < umbra^2.  Here, per accepted step:
+//   1. the window is computed with the reference's own IEEE operations (sub, sub, div, floor; the quotient
+//      goes through a reciprocal and is re-divided exactly only next to an integer, floor_div);
+//   2. SCAN-LINE ROWS: on each row the capsule is an interval whose ends are closed-form (cap a, straight
+//      edge, or cap b); every node strictly between the ends is marked with two shifts.  FP32, relative to
+//      endpoint a.  Nodes within the FP32 error bound of an end (~1e-4 of the rows) go to 3;
+//   3. NODE TEST (also the whole row for near-tangent rows, near-horizontal or sub-1e-10 m segments):
+//      t = sat(dot/len^2), p = c - t b, d2 = |p|^2 in FP32.  |d2_fp32 - d2_exact| <= 44 eps32 L^2 with
+//      L = max(|bax|,|bay|) + umbra + max(dx,dy) >= every |cax|,|cay| of the window (derivation in DESIGN.md);
+//      the reference's own FP64 value is within 32 eps64 (..)^2 of exact, 2^-29 times smaller.  Band
+//      E = 128 eps32 L^2:   d2 < umbra^2 - E -> inside,   d2 > umbra^2 + E -> outside   (the reference's answers),
+//      otherwise (incl. nan) -> the reference's formula in unfused FP64 (exact_distancesquared);
+//   4. the row's bits are OR-ed into the realization's bitmap with one or two RED.OR (L2, no return value).
+// Zero-length segments set nothing (0/0 = nan in :421).  Bit-exact against the executed reference.
 
 __device__ __forceinline__ double exact_distancesquared(double ax, double ay, double bx, double by, double cx, double cy)
 {
