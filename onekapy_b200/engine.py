@@ -271,6 +271,20 @@ class Engine:
             status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
         m = spec.model_desc()
         lat = geom.as_lattice(spec.umbra) if geom is not None else None
+        nvtx = self.torch.cuda.nvtx if os.environ.get("ONEKA_NVTX") else None      # ranges for nsys / ncu --nvtx
+        if nvtx:
+            nvtx.range_push("oneka.capture R=%d P=%d %s" % (R, P, "track+raster" if lat is not None else "track"))
+        try:
+            self._capture_call(spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P)
+        finally:
+            if nvtx:
+                nvtx.range_pop()
+        if per_path:
+            return dict(end_xy=end_xy, nverts=nverts, status=status)
+        return None
+
+    def _capture_call(self, spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P):
+        torch = self.torch
         if clip is not None:
             if lat is None or counts is None:
                 raise ValueError("clip needs a lattice and a count grid")
@@ -286,9 +300,6 @@ class Engine:
                 _ptr(dp.q[r0:r1]), _ptr(dp.cond[r0:r1]), _ptr(dp.poro[r0:r1]), _ptr(dp.thick[r0:r1]), _ptr(dp.coef[r0:r1]),
                 _ptr(dp.start_xy), _ptr(counts) if (counts is not None and lat is not None) else None,
                 _ptr(end_xy), _ptr(nverts), _ptr(status)))
-        if per_path:
-            return dict(end_xy=end_xy, nverts=nverts, status=status)
-        return None
 
     # -- exact emulation of the auto-expanding field (probabilityfield.py:298-301, 335) -----------------
     def path_bboxes(self, spec: FlowSpec, dp: DeviceParams):
