@@ -15,6 +15,7 @@ Reference map (file:line under the reference tree):
                     auto-expanding ProbabilityField would end with (probabilityfield.py:229-245)
 """
 import ctypes as C
+import functools
 import os
 from dataclasses import dataclass, field
 from typing import Optional
@@ -79,17 +80,23 @@ class RealizationParams:
         return RealizationParams(self.q[s], self.cond[s], self.poro[s], self.thick[s], self.coef[s])
 
 
-def start_ring(xtarget, ytarget, rtarget, npaths):
-    """Start points on the circle of radius rtarget + 1 m (oneka/capturezone.py:110-115).
-
-    Evaluated scalar by scalar with NumPy, as the reference does, so that cos/sin round
-    identically; the points are the same for every realization."""
+@functools.lru_cache(maxsize=16)
+def _start_ring_cached(xtarget, ytarget, rtarget, npaths):
     STEPAWAY = 1.0
     out = np.empty((npaths, 2), dtype=np.float64)
     for i, theta in enumerate(np.linspace(0, 2 * np.pi, npaths + 1)[0:-1]):
         out[i, 0] = (rtarget + STEPAWAY) * np.cos(theta) + xtarget
         out[i, 1] = (rtarget + STEPAWAY) * np.sin(theta) + ytarget
+    out.setflags(write=False)
     return out
+
+
+def start_ring(xtarget, ytarget, rtarget, npaths):
+    """Start points on the circle of radius rtarget + 1 m (oneka/capturezone.py:110-115).
+
+    Evaluated scalar by scalar with NumPy, as the reference does, so that cos/sin round
+    identically; the points are the same for every realization (cached, read-only)."""
+    return _start_ring_cached(float(xtarget), float(ytarget), float(rtarget), int(npaths))
 
 
 def _ptr(t):
