@@ -120,7 +120,7 @@ class DeviceParams:
         self.thick = torch.as_tensor(params.thick, dtype=f64).to(device)
         self.coef = torch.as_tensor(params.coef, dtype=f64).to(device)
         self.well_xy = torch.as_tensor(np.ascontiguousarray(well_xy, dtype=np.float64)).to(device)
-        self.start_xy = torch.as_tensor(np.ascontiguousarray(start_xy, dtype=np.float64)).to(device)
+        self.start_xy = torch.as_tensor(np.array(start_xy, dtype=np.float64, order="C", copy=True)).to(device)   # the cached ring is read-only
 
 
 class Engine:
