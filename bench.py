@@ -12,7 +12,7 @@ NCCL allreduce of the count grid) over one batch of pre-sampled realization rows
                 (BASELINE.json configs[3] is 1M realizations over 8 GPUs = 61 such steps per GPU)
   c1            data/basic.py, 100 x 100 (the reference's CPU-runnable case)
   c5            data/basic.py field on a fine lattice (spacing 4, umbra 20 -> ~15x15-node windows, a
-                4096 x 4096-class grid), 256 realizations x 1000 paths: rasterisation stress
+                4096 x 4096-class grid), 2048 realizations x 1000 paths: rasterisation stress
 
 metric = particle-steps/s = DOPRI5 attempts per second summed over all particles and GPUs;
 realizations/s is reported beside it.  Weak scaling: per-GPU work is fixed as N grows.
@@ -64,7 +64,7 @@ def make_workload(name, realizations, npaths, seed):
     elif name == "c5":
         pb = problems.load("basic")
         pb["spacing"], pb["umbra"] = 4.0, 20.0          # ~13 x 17 km of capture zones -> a 4096 x 4096-class lattice
-        R = realizations or 256
+        R = realizations or 2048
         P = npaths or 1000
         label = "C5 basic field on a fine lattice (spacing 4, umbra 20: ~15x15-node windows, 4096^2-class grid), %d realizations x %d paths per GPU per step" % (R, P)
     else:

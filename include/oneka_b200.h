@@ -139,6 +139,20 @@ int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice
                   const double *coef_dev, const double *start_xy_dev,
                   uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev);
 
+/* ---- Guarded capture: the lattice was only estimated ------------------------------------- *
+ * Same as oneka_capture, but a realization one of whose segments had its window clipped by the
+ * LATTICE EDGE (it left the estimated extents) is not registered: clipped_dev[r] is set to 1 (0
+ * otherwise) and its bitmap is discarded -- the analogue of ProbabilityField.reset()
+ * (oneka/probabilityfield.py:362-376, "discarding a partially processed invalid realization").
+ * The caller re-runs just those realizations on a lattice grown to the bounding box reported by
+ * oneka_read_stats, instead of repeating the whole run (Engine.run).                            */
+int oneka_capture_guarded(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
+                          uint32_t *clipped_dev);
+
 /* ---- Exact emulation of the reference's auto-expanding field ----------------------------- *
  * The reference expands its grid to each trace's bounding box just before inserting it
  * (ProbabilityField.rasterize, oneka/probabilityfield.py:335) and insert() clips every segment's

@@ -20,7 +20,7 @@ SYMBOLS = [
     "oneka_set_workspace_limit", "oneka_synchronize", "oneka_launch_count", "oneka_set_profiling",
     "oneka_kernel_ms", "oneka_eval_points_host", "oneka_trace", "oneka_raster_traces", "oneka_capture",
     "oneka_read_stats", "oneka_reset_stats", "oneka_capture_host", "oneka_fp64_probe", "oneka_path_bboxes",
-    "oneka_capture_clipped", "oneka_count_histogram", "oneka_gaussian_smooth",
+    "oneka_capture_clipped", "oneka_count_histogram", "oneka_gaussian_smooth", "oneka_capture_guarded",
 ]
 
 
@@ -88,6 +88,8 @@ def load():
     L.oneka_path_bboxes.argtypes = [_vp, C.POINTER(ModelDesc), _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp]
     L.oneka_capture_clipped.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.oneka_capture_guarded.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.oneka_count_histogram.argtypes = [_vp, _vp, C.c_int64, C.c_int32, _vp]
     L.oneka_gaussian_smooth.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp, _vp]

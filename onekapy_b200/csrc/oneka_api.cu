@@ -118,7 +118,8 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
 // in registers, bitmap words are zeroed as they are consumed, counts get one RED per nonzero
 // counter.  Reads are coalesced (consecutive threads = consecutive words of one slot).
 __global__ void __launch_bounds__(256)
-flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, LatticeDev L, unsigned int *counts)
+flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, LatticeDev L, unsigned int *counts,
+             const unsigned int *slot_flags)
 {
     const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= L.words) return;
@@ -133,6 +134,7 @@ flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, Lat
         const unsigned int v = *pw;
         if (v) {
             *pw = 0u;
+            if (slot_flags != nullptr && slot_flags[s]) continue;    // guarded mode: a clipped realization is not registered
             any = true;
 #pragma unroll
             for (int b = 0; b < 32; ++b) cnt[b] += (v >> b) & 1u;
@@ -360,7 +362,8 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     return ONEKA_OK;
 }
 
-static int launch_flush(oneka_ctx *ctx, const LatticeDev &L, long long nslots, unsigned int *counts)
+static int launch_flush(oneka_ctx *ctx, const LatticeDev &L, long long nslots, unsigned int *counts,
+                        const unsigned int *slot_flags = nullptr)
 {
     const unsigned gx = (unsigned)((L.words + 255) / 256);
     // aim for >= 2 waves of 148 SMs x 8 CTAs
@@ -371,7 +374,7 @@ static int launch_flush(oneka_ctx *ctx, const LatticeDev &L, long long nslots, u
     const long long per_y = (nslots + want_y - 1) / want_y;
     const unsigned gy = (unsigned)((nslots + per_y - 1) / per_y);
     prof_begin(ctx, 1);
-    flush_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(ctx->bitmaps, nslots, per_y, L, counts);
+    flush_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(ctx->bitmaps, nslots, per_y, L, counts, slot_flags);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -629,7 +632,7 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
                   const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
                   const double *coef_dev, const double *start_xy_dev,
                   uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
-                  const int32_t *clip_dev, double *path_bbox_dev)
+                  const int32_t *clip_dev, double *path_bbox_dev, uint32_t *flags_dev = nullptr)
 {
     if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
     int rc = check_model(m);
@@ -665,10 +668,11 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
         tp.status = status_dev ? status_dev + (size_t)r0 * P : nullptr;
         tp.clip = clip_dev ? clip_dev + 4 * (size_t)r0 * P : nullptr;
         tp.path_bbox = path_bbox_dev ? path_bbox_dev + 4 * (size_t)r0 * P : nullptr;
+        tp.slot_flags = (raster && flags_dev) ? flags_dev + r0 : nullptr;
         if (raster) {
             rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps);
             if (rc) return rc;
-            rc = launch_flush(ctx, L, nr, counts_dev);
+            rc = launch_flush(ctx, L, nr, counts_dev, tp.slot_flags);
             if (rc) return rc;
         } else {
             rc = launch_track<0>(ctx, m, tp, L, nullptr);
@@ -686,6 +690,22 @@ int oneka_capture(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice
 {
     return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
                         counts_dev, end_xy_dev, nverts_dev, status_dev, nullptr, nullptr);
+}
+
+int oneka_capture_guarded(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
+                          uint32_t *clipped_dev)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (R == 0) return ONEKA_OK;
+    if (!clipped_dev || !lat || !counts_dev) return fail(ONEKA_ERR_ARG, "oneka_capture_guarded needs clipped_dev, lat and counts_dev");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(clipped_dev, 0, (size_t)R * sizeof(uint32_t), ctx->stream));
+    return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
+                        counts_dev, end_xy_dev, nverts_dev, status_dev, nullptr, nullptr, clipped_dev);
 }
 
 int oneka_path_bboxes(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy_dev, int64_t R, int32_t P,

@@ -50,6 +50,8 @@ struct TrackParams {
     double *end_xy; int *nverts; unsigned char *status; int *attempts;
     double *path_bbox;               // [R][P][4] min x, max x, min y, max y of each path's vertices, or null
     const int *clip;                 // [R][P][4] per-path raster clip window (left, right, bottom, top), or null
+    unsigned int *slot_flags;        // [R] set to 1 when any segment of the realization was clipped by the lattice edge
+                                     //     (such realizations are not registered by the flush; oneka_capture_guarded), or null
     // oneka_trace only
     double *verts; int max_verts;
     // statistics
@@ -556,6 +558,11 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         if (tp.status) tp.status[g] = (unsigned char)status;
         if (tp.attempts) tp.attempts[g] = nattempt;
         if (tp.path_bbox) { double *pb = tp.path_bbox + 4 * g; pb[0] = bx0; pb[1] = bx1; pb[2] = by0; pb[3] = by1; }
+    }
+
+    // ---- guarded mode: tell the flush (and the host) that this realization ran off the lattice ----
+    if (MODE == 1 && tp.slot_flags != nullptr) {
+        if (__any_sync(0xffffffffu, ctr.clipped != 0) && (threadIdx.x & 31) == 0) atomicOr(tp.slot_flags + r, 1u);
     }
 
     // ---- statistics: warp-reduce, one atomic per warp per word ----

@@ -122,6 +122,18 @@ class DeviceParams:
         self.well_xy = torch.as_tensor(np.ascontiguousarray(well_xy, dtype=np.float64)).to(device)
         self.start_xy = torch.as_tensor(np.array(start_xy, dtype=np.float64, order="C", copy=True)).to(device)   # the cached ring is read-only
 
+    def select(self, idx):
+        """The rows `idx` (int64 device tensor) as a new DeviceParams sharing wells and start ring."""
+        sub = object.__new__(DeviceParams)
+        sub.R = int(idx.numel())
+        sub.q = self.q.index_select(0, idx).contiguous()
+        sub.cond = self.cond.index_select(0, idx).contiguous()
+        sub.poro = self.poro.index_select(0, idx).contiguous()
+        sub.thick = self.thick.index_select(0, idx).contiguous()
+        sub.coef = self.coef.index_select(0, idx).contiguous()
+        sub.well_xy, sub.start_xy = self.well_xy, self.start_xy
+        return sub
+
 
 class Engine:
     """One context per GPU (oneka_ctx)."""
@@ -263,11 +275,12 @@ class Engine:
         return self.torch.zeros((geom.nrows, geom.ncols), dtype=self.torch.int32, device=self.device)
 
     def capture(self, spec: FlowSpec, dp: DeviceParams, geom: Optional[LatticeGeom] = None, counts=None,
-                per_path=False, r0=0, r1=None, clip=None):
+                per_path=False, r0=0, r1=None, clip=None, flags=None):
         """Enqueue track + rasterise + register for realizations [r0, r1) of `dp` (asynchronous).
 
         geom/counts None -> tracking only.  clip: int32 device tensor [R, P, 4] of per-path raster windows
-        (oneka_capture_clipped).  Returns the per-path tensors (or None)."""
+        (oneka_capture_clipped).  flags: int32 device tensor [R]; realizations that ran off the lattice are
+        flagged and NOT registered (oneka_capture_guarded).  Returns the per-path tensors (or None)."""
         torch = self.torch
         r1 = dp.R if r1 is None else r1
         R, P = r1 - r0, int(dp.start_xy.shape[0])
@@ -282,7 +295,7 @@ class Engine:
         if nvtx:
             nvtx.range_push("oneka.capture R=%d P=%d %s" % (R, P, "track+raster" if lat is not None else "track"))
         try:
-            self._capture_call(spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P)
+            self._capture_call(spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags)
         finally:
             if nvtx:
                 nvtx.range_pop()
@@ -290,9 +303,18 @@ class Engine:
             return dict(end_xy=end_xy, nverts=nverts, status=status)
         return None
 
-    def _capture_call(self, spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P):
+    def _capture_call(self, spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags=None):
         torch = self.torch
-        if clip is not None:
+        if flags is not None:
+            if clip is not None or lat is None or counts is None:
+                raise ValueError("flags needs a lattice and a count grid, and excludes clip")
+            if tuple(flags.shape) != (dp.R,) or flags.dtype != torch.int32 or not flags.is_contiguous():
+                raise ValueError("flags must be a contiguous int32 tensor [R]")
+            _cabi.check(self._L.oneka_capture_guarded(
+                self._h, C.byref(m), C.byref(lat), _ptr(dp.well_xy), R, P,
+                _ptr(dp.q[r0:r1]), _ptr(dp.cond[r0:r1]), _ptr(dp.poro[r0:r1]), _ptr(dp.thick[r0:r1]), _ptr(dp.coef[r0:r1]),
+                _ptr(dp.start_xy), _ptr(counts), _ptr(end_xy), _ptr(nverts), _ptr(status), _ptr(flags[r0:r1])))
+        elif clip is not None:
             if lat is None or counts is None:
                 raise ValueError("clip needs a lattice and a count grid")
             if tuple(clip.shape) != (dp.R, P, 4) or clip.dtype != torch.int32 or not clip.is_contiguous():
@@ -423,8 +445,10 @@ class Engine:
         2. lattice = reference lattice (anchored at target - spacing, probabilityfield.py:140-146)
            expanded to the pilot box plus `margin` of its size on every side (a larger lattice only
            costs bitmap memory; the result does not depend on it);
-        3. fused capture on that lattice; the kernel reports the true bounding box of every vertex and,
-           if any fell outside the lattice, the pass is repeated once on the exact box;
+        3. fused GUARDED capture on that lattice: a realization any of whose segments is clipped by the lattice
+           edge is flagged and not registered (oneka_capture_guarded); the kernel also reports the true bounding
+           box of every vertex.  Only the flagged realizations (Monte-Carlo outliers, typically a handful) are
+           tracked again, on the exact final extents, into a grid that carries the first pass's counts over;
         4. (multi-GPU) bounding boxes min/max-reduced, count grids summed with ONE allreduce;
         5. crop to the reference's final extents (probabilityfield.py:229-245).
 
@@ -448,22 +472,30 @@ class Engine:
             return self._empty_result(spec)              # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
         if not np.all(np.isfinite(bbox)):
             raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
-        pad = margin
-        for attempt in range(3):
-            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
-            pw, ph = pad * max(w, spec.umbra), pad * max(h, spec.umbra)
-            grow = (bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
-            geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(*grow)
-            counts = self.new_counts(geom)
-            self.reset_stats()
-            pp = self.capture(spec, dp, geom, counts, per_path=per_path)
-            stats = self.read_stats()
-            true_bbox = parallel.reduce_bbox(stats["bbox"], group, dev)
-            if geom.strictly_contains(true_bbox):
-                break
-            bbox, pad = true_bbox, 0.0          # now exact: the second pass is guaranteed to fit
-        else:
-            raise OnekaError("lattice did not converge")
+        # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
+        w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+        pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
+        geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
+            bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+        counts = self.new_counts(geom)
+        flags = self.torch.zeros(R, dtype=self.torch.int32, device=self.device)
+        self.reset_stats()
+        pp = self.capture(spec, dp, geom, counts, per_path=per_path, flags=flags)
+        stats = self.read_stats()
+        true_bbox = parallel.reduce_bbox(stats["bbox"], group, dev)
+        nflag = int(flags.sum().item()) if R else 0
+        stats["rerun_realizations"] = nflag
+        rerun = parallel.any_rank(nflag > 0, group, dev)
+        if rerun:
+            # ... and only those are tracked again, on the exact final extents; pass-1 counts are carried over
+            final = final_geometry(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget, true_bbox)
+            counts2 = self.new_counts(final)
+            _copy_overlap(counts, geom, counts2, final)
+            if nflag:
+                self.capture(spec, dp.select(flags.nonzero().reshape(-1)), final, counts2)
+            counts, geom = counts2, final
+        elif not geom.strictly_contains(true_bbox):
+            raise OnekaError("internal: a vertex left the lattice but no realization was flagged")
         if group is not None:
             parallel.allreduce_counts(counts, group)
             total = parallel.sum_int(R, group, self.device)
@@ -475,6 +507,16 @@ class Engine:
         if per_path:
             pp = {k: v.cpu().numpy() for k, v in pp.items()}
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
+
+
+def _copy_overlap(src, src_geom, dst, dst_geom):
+    """dst += nothing; dst[overlap] = src[overlap] for two grids on the same lattice (integer node offsets)."""
+    dj = int(round((dst_geom.xmin - src_geom.xmin) / src_geom.deltax))     # dst node (., 0) is src column dj
+    di = int(round((dst_geom.ymin - src_geom.ymin) / src_geom.deltay))
+    j0, j1 = max(0, dj), min(src_geom.ncols, dj + dst_geom.ncols)
+    i0, i1 = max(0, di), min(src_geom.nrows, di + dst_geom.nrows)
+    if j0 < j1 and i0 < i1:
+        dst[i0 - di:i1 - di, j0 - dj:j1 - dj] = src[i0:i1, j0:j1]
 
 
 _DEFAULT = None

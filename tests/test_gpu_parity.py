@@ -356,6 +356,12 @@ def test_run_with_subsampled_pilot(eng, golden):
     b = eng.run(spec, par, pilot=2, margin=0.0, pilot_paths=2)      # margin 0 forces the grow-and-repeat branch
     c = eng.run(spec, par, pilot=3, margin=2.0)
     assert b["work_geom"] != a["work_geom"] and c["work_geom"] != a["work_geom"]
+    assert a["stats"]["rerun_realizations"] == 0 and c["stats"]["rerun_realizations"] == 0
+    assert 0 < b["stats"]["rerun_realizations"] <= len(par)
+    # a lattice that fits most but not all realizations: only the outliers are tracked again
+    d = eng.run(spec, par, pilot=3, margin=0.0, pilot_paths=10)     # lattice from realizations 0, 2, 4 only
+    assert 0 < d["stats"]["rerun_realizations"] <= len(par)
+    assert d["geom"] == a["geom"] and np.array_equal(d["counts"], a["counts"])
     for r in (b, c):
         assert r["geom"] == a["geom"] and np.array_equal(r["counts"], a["counts"])
 
