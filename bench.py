@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_workload(name, realizations, npaths, seed):
+def make_workload(name, realizations, npaths, seed, unconfined=False):
     from onekapy_b200 import problems, synthetic
     from onekapy_b200.engine import FlowSpec
     if name == "c3":
@@ -69,6 +69,9 @@ def make_workload(name, realizations, npaths, seed):
         label = "C5 basic field on a fine lattice (spacing 4, umbra 20: ~15x15-node windows, 4096^2-class grid), %d realizations x %d paths per GPU per step" % (R, P)
     else:
         raise SystemExit("unknown workload %r" % name)
+    if unconfined:
+        pb["confined"] = False
+        label += ", confined=False"
     params = synthetic.sample_rows_fast(pb, R, seed)
     xt, yt, rt = pb["wells"][pb["target"]][0:3]
     spec = FlowSpec(well_xy=np.array([[w[0], w[1]] for w in pb["wells"]], dtype=float), xtarget=float(xt),
@@ -181,7 +184,7 @@ def run_reference_arm(args):
         return
     from oracle import oracle as O
     O.build()
-    spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed)
+    spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed, args.unconfined)
     geom = cpu_geom(spec, params)
     # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the
     # reference arm on one core at N > 1
@@ -235,7 +238,7 @@ def run_ours(args):
         dist.barrier()
     eng = Engine(local)
     dev = eng.device
-    spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed + rank)
+    spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed + rank, args.unconfined)
     R, P, nw = len(params), spec.npaths, len(spec.well_xy)
 
     def barrier():
@@ -375,6 +378,7 @@ def main():
     ap.add_argument("--npaths", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20200725)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--unconfined", action="store_true", help="confined=False: the head-dependent velocity of model.py:353-389")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

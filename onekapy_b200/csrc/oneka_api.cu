@@ -68,15 +68,20 @@ struct oneka_ctx {
 // ------------------------------------------------------------------------------------------
 // Kernels
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cf_F(const TrackParams &tp, long long r) { return tp.coef[6 * r + 5]; }
+
 template <bool CONFINED>
 __device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc,
                                                   double2 *s_wxy, double *s_w)
 {
     const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
     const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
+    float *s_w32 = const_cast<float *>(w32_of(s_w, tp.nw));
     for (int i = threadIdx.x; i < tp.nw; i += blockDim.x) {
         s_wxy[i] = make_double2(tp.well_xy[2 * i], tp.well_xy[2 * i + 1]);
-        s_w[i] = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;     // q/(2 pi) [/(H n)]
+        const double w = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;    // q/(2 pi) [/(H n)]
+        s_w[i] = w;
+        if (!CONFINED) s_w32[i] = (float)w;
     }
     if (threadIdx.x == 0) {
         const double *cf = tp.coef + 6 * r;
@@ -88,9 +93,20 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
         rc.A = cf[0]; rc.B = cf[1]; rc.F = cf[5];
         rc.k = k; rc.H = H; rc.n = n;
         rc.half_kH2 = 0.5 * k * (H * H);
+        rc.inv_Hn = 1.0 / (H * n);
         rc.xo = tp.xo; rc.yo = tp.yo;
     }
     __syncthreads();
+    if (!CONFINED) {
+        // error bound of the FP32 screening sum: per term <= |w| (47 * 2^-23 * 2 + 2^-22) log2 units, accumulation
+        // <= nw * 2^-24 * 47 sum|w|; times 0.5 ln 2, with a 5x margin:  2e-5 (nw + 16) sum|w|
+        if (threadIdx.x == 0) {
+            double sw = 0.0;
+            for (int i = 0; i < tp.nw; ++i) sw += fabs(s_w[i]);
+            rc.pot_err = 2e-5 * (double)(tp.nw + 16) * sw + 1e-9 * fabs(cf_F(tp, r));
+        }
+        __syncthreads();
+    }
 }
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
@@ -181,7 +197,7 @@ eval_points_kernel(TrackParams tp, long long npts, const double *pts, double *ou
     __shared__ RealConsts rc_c, rc_u;
     double2 *s_wxy = s_dyn;
     double *s_wc = reinterpret_cast<double *>(s_dyn + tp.nw);
-    double *s_wu = s_wc + tp.nw;
+    double *s_wu = s_wc + ((tp.nw + 1) & ~1) + (tp.nw + 1) / 2 + 2;      // past s_wc and the (unused) float slot behind it
     stage_realization<true>(tp, 0, rc_c, s_wxy, s_wc);
     stage_realization<false>(tp, 0, rc_u, s_wxy, s_wu);
     for (long long i = threadIdx.x; i < npts; i += blockDim.x) {
@@ -312,7 +328,8 @@ static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_d
 
 // + 32 B: ptxas widens the scaled-discharge loads of the remainder iterations to LDS.128 (w[i], w[i+1]); with an odd
 // number of wells the second half lies 8 bytes past w[nw-1].  Harmless on hardware, but compute-sanitizer flags it.
-static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double)) + 32; }
+// + nw floats (+ alignment): FP32 copies of the scaled discharges for the unconfined screening sum.
+static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double) + sizeof(float)) + 64; }
 
 static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
 {
@@ -563,7 +580,7 @@ int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const doub
         if (!(mm.tol > 0)) mm.tol = 1.0;
         if (!(mm.maxstep > 0)) mm.maxstep = 1.0;
         TrackParams tp = make_track(&mm, d_wxy, 1, 1, d_q, d_k, d_n, d_H, d_cf, nullptr, ctx->stats_dev);
-        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * sizeof(double)) + 32;
+        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * (sizeof(double) + sizeof(float))) + 160;
         if (smem > 48 * 1024) TRY2(cudaFuncSetAttribute(eval_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_points_kernel<<<1, 128, smem, s>>>(tp, npts, d_pts, d_out);
         ctx->launches++;

@@ -33,8 +33,16 @@ struct RealConsts {
     double A, B, F;                  // potential terms (model.py:226-231)
     double k, H, n;                  // conductivity, thickness, porosity
     double half_kH2;                 // 0.5*k*H^2 (model.py:345)
+    double inv_Hn;                   // 1/(H n): the velocity scale wherever head >= H
+    double pot_err;                  // bound on |Phi_fp32 - Phi| of the screening sum (see field_feval<false>)
     double xo, yo;
 };
+
+// the FP32 copies of the scaled discharges live right behind the FP64 ones in shared memory (unconfined only)
+__device__ __forceinline__ const float *w32_of(const double *s_w, int nw)
+{
+    return reinterpret_cast<const float *>(s_w + ((nw + 1) & ~1));
+}
 
 struct TrackParams {
     int nw;
@@ -128,7 +136,10 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
     const double dy0 = y - rc.yo;
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
-    double lsum = 0.0;
+    // unconfined: FP32 screening sum of  w_i log2(r_i^2)  (MUFU.LG2 on the XU pipe; the exact FP64 logs below are
+    // needed only where the aquifer is not fully saturated)
+    const float *s_w32 = CONFINED ? nullptr : w32_of(s_w, nw);
+    float lsum32 = 0.0f;
 #pragma unroll WELL_UNROLL
     for (int i = 0; i < nw; ++i) {
         const double2 wxy = s_wxy[i];
@@ -142,16 +153,33 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
         const double s = fma(s0, t, s0);
         gx = fma(s, dx, gx);
         gy = fma(s, dy, gy);
-        if (!CONFINED) lsum = fma(w, log(r2), lsum);
+        if (!CONFINED) lsum32 = fmaf(s_w32[i], __log2f((float)r2), lsum32);
     }
     if (CONFINED) {
         fx = gx;
         fy = gy;
         return PATH_OK;
     } else {
-        // potential (model.py:226-237); 0.5*lsum = sum q ln(r2)/(4 pi) since w = q/(2 pi)
-        double pot = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
-        pot = fma(0.5, lsum, pot);
+        // regional part of the potential (model.py:226-231)
+        const double pot_reg = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
+        // Phi >= k H^2/2  <=>  head >= H  (model.py:345-349), and then V = Q/(H n) whatever Phi is (model.py:382-384;
+        // at head == H both branches of :382-387 give the same value).  The screening sum decides that case:
+        // sum q ln(r^2)/(4 pi) = 0.5 ln2 sum w log2(r^2), |error| <= pot_err (set when the realization is staged).
+        const double pot_apx = fma(0.34657359027997264, (double)lsum32, pot_reg);
+        if (pot_apx - rc.pot_err > rc.half_kH2) {
+            fx = gx * rc.inv_Hn;
+            fy = gy * rc.inv_Hn;
+            return PATH_OK;
+        }
+        // not (certainly) saturated: the reference's potential with FP64 logs (model.py:259-266)
+        double lsum = 0.0;
+        for (int i = 0; i < nw; ++i) {
+            const double2 wxy = s_wxy[i];
+            const double dx = x - wxy.x;
+            const double dy = y - wxy.y;
+            lsum = fma(s_w[i], log(fma(dy, dy, dx * dx)), lsum);
+        }
+        const double pot = fma(0.5, lsum, pot_reg);                     // 0.5*lsum = sum q ln(r2)/(4 pi) since w = q/(2 pi)
         if (!(pot > 0.0)) return PATH_AQUIFER_DRY;                      // model.py:343-344 (nan also ends the trace)
         double head;
         if (pot < rc.half_kH2) head = sqrt(2.0 * pot / rc.k);           // model.py:345-346
