@@ -435,7 +435,7 @@ class Engine:
                     work_geom=g)
 
     # -- the public flow -----------------------------------------------------------------------
-    def run(self, spec: FlowSpec, params: RealizationParams, pilot=256, margin=0.5, group=None, per_path=False,
+    def run(self, spec: FlowSpec, params: RealizationParams, pilot=256, margin=0.25, group=None, per_path=False,
             pilot_paths=128):
         """Capture-zone count grid for all realizations in `params` (this rank's shard when `group`
         is a torch.distributed process group), on the extents the reference would end with.
