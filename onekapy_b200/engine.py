@@ -150,6 +150,7 @@ class Engine:
         torch.cuda.set_device(self.device)
         self._L = _cabi.load()
         self._h = _cabi.create(self.index)
+        self._geom_hint = {}
         self.use_stream(torch.cuda.current_stream(self.device))
         if workspace_limit is not None:
             _cabi.check(self._L.oneka_set_workspace_limit(self._h, int(workspace_limit)))
@@ -267,7 +268,7 @@ class Engine:
     # -- the hot path, device-resident ----------------------------------------------------------
     def new_counts(self, geom: LatticeGeom):
         need = 4 * int(geom.nrows) * int(geom.ncols)
-        free, _ = self.torch.cuda.mem_get_info(self.device)
+        free = self.torch.cuda.mem_get_info(self.device)[0] if need > (1 << 30) else need      # the query costs ~1 ms
         if need > free:
             raise OnekaError("count grid %d x %d needs %.1f GiB but %.1f GiB are free: the bounding box of the traces is "
                              "implausibly large for this spacing (a realization ran away?)"
@@ -436,7 +437,7 @@ class Engine:
 
     # -- the public flow -----------------------------------------------------------------------
     def run(self, spec: FlowSpec, params: RealizationParams, pilot=256, margin=0.25, group=None, per_path=False,
-            pilot_paths=128):
+            pilot_paths=128, reuse_lattice=True):
         """Capture-zone count grid for all realizations in `params` (this rank's shard when `group`
         is a torch.distributed process group), on the extents the reference would end with.
 
@@ -458,25 +459,34 @@ class Engine:
         start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
         dp = self.upload(spec, params, start)
         dev = self.device if group is not None else None
-        # 1. pilot
+        # 1. pilot (skipped when this engine has already seen the same problem: the lattice of the previous call is
+        #    reused as the estimate -- chunked runs of one problem pay for the pilot once; the guarded capture below
+        #    makes a poor estimate cost a partial re-run, never a wrong grid)
+        key = (spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths, spec.duration, spec.spacing, spec.umbra, spec.confined,
+               spec.tol, spec.maxstep, spec.well_xy.tobytes())
+        hint = self._geom_hint.get(key) if reuse_lattice else None      # every rank makes the same calls, so the caches agree
         self.reset_stats()
-        if R > 0:
+        if R > 0 and hint is None:
             rstep = max(1, R // max(1, pilot))
             pstep = max(1, spec.npaths // max(1, pilot_paths))
             if rstep == 1 and pstep == 1:
                 self.capture(spec, dp)
             else:
                 self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
-        bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, dev)
         if parallel.sum_int(R, group, dev) == 0:
             return self._empty_result(spec)              # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
-        if not np.all(np.isfinite(bbox)):
-            raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
         # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
-        w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
-        pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
-        geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
-            bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+        if hint is not None:
+            geom = hint
+        else:
+            bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, dev)
+            if not np.all(np.isfinite(bbox)):
+                raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
+            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+            pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
+            geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
+                bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+        work_geom = geom
         counts = self.new_counts(geom)
         flags = self.torch.zeros(R, dtype=self.torch.int32, device=self.device)
         self.reset_stats()
@@ -506,6 +516,8 @@ class Engine:
         out = counts[i0:i0 + final.nrows, j0:j0 + final.ncols].contiguous().cpu().numpy().view(np.uint32)
         if per_path:
             pp = {k: v.cpu().numpy() for k, v in pp.items()}
+        if reuse_lattice and not rerun:
+            self._geom_hint[key] = work_geom             # it fitted every realization: a good estimate for the next call
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
 
 

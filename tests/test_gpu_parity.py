@@ -352,16 +352,31 @@ def test_run_with_subsampled_pilot(eng, golden):
     """pilot < R: the lattice comes from a subsample + margin; result must not depend on it."""
     g = golden("sto_basic.npz")
     s, spec, par = spec_of(g)
-    a = eng.run(spec, par)
-    b = eng.run(spec, par, pilot=2, margin=0.0, pilot_paths=2)      # margin 0 forces the grow-and-repeat branch
-    c = eng.run(spec, par, pilot=3, margin=2.0)
+    a = eng.run(spec, par, reuse_lattice=False)
+    b = eng.run(spec, par, pilot=2, margin=0.0, pilot_paths=2, reuse_lattice=False)      # margin 0 forces re-tracking
+    c = eng.run(spec, par, pilot=3, margin=2.0, reuse_lattice=False)
     assert b["work_geom"] != a["work_geom"] and c["work_geom"] != a["work_geom"]
     assert a["stats"]["rerun_realizations"] == 0 and c["stats"]["rerun_realizations"] == 0
     assert 0 < b["stats"]["rerun_realizations"] <= len(par)
     # a lattice that fits most but not all realizations: only the outliers are tracked again
-    d = eng.run(spec, par, pilot=3, margin=0.0, pilot_paths=10)     # lattice from realizations 0, 2, 4 only
+    d = eng.run(spec, par, pilot=3, margin=0.0, pilot_paths=10, reuse_lattice=False)     # lattice from realizations 0, 2, 4 only
     assert 0 < d["stats"]["rerun_realizations"] <= len(par)
     assert d["geom"] == a["geom"] and np.array_equal(d["counts"], a["counts"])
+    # lattice reuse: the second call with the same problem skips the pilot pass (one launch fewer) and agrees
+    e1 = eng.run(spec, par)
+    n0 = eng.launch_count()
+    e2 = eng.run(spec, par)
+    assert eng.launch_count() - n0 == 2 and e2["work_geom"] == e1["work_geom"]
+    assert e2["geom"] == a["geom"] and np.array_equal(e2["counts"], a["counts"])
+    # ... and a stale estimate (here: from a quarter of the duration) only costs a partial re-run
+    import copy
+    short = copy.copy(spec)
+    short.duration = spec.duration / 4
+    small = eng.run(short, par)["work_geom"]
+    key_dur = [k for k in eng._geom_hint if k[4] == short.duration][0]
+    eng._geom_hint[tuple(spec.duration if i == 4 else v for i, v in enumerate(key_dur))] = small
+    f = eng.run(spec, par)
+    assert f["stats"]["rerun_realizations"] > 0 and f["geom"] == a["geom"] and np.array_equal(f["counts"], a["counts"])
     for r in (b, c):
         assert r["geom"] == a["geom"] and np.array_equal(r["counts"], a["counts"])
 
