@@ -22,8 +22,8 @@ the device with CUDA events on the launching stream, max over ranks.  L2 is flus
 write) before every timed step; the flush is inside the bracket (40 us against >100 ms steps).
 `e2e` times the public call Engine.run() with HOST buffers: H2D of the parameter rows from pinned
 memory, guarded capture on the estimated lattice, (allreduce,) crop and D2H of the count grid,
-every step; the pilot pass that estimates the lattice runs on the first (warm-up) call only, later
-calls with the same problem reuse its lattice.
+EVERY step, including the pilot pass that estimates the lattice (reuse_lattice=False: nothing is carried
+over from one timed call to the next; the pilot's attempts are not counted as work, its time is).
 `roofline` is the fused tracking+raster kernel against the FP64 pipe: algorithmic flops per
 attempt = 257 + 90*Nw over the kernel's CUDA-event time, divided by an FP64
 DFMA probe measured in the same process (MEASURED_PEAKS.json carries no FP64 figure).
@@ -319,14 +319,16 @@ def run_ours(args):
     from onekapy_b200.engine import RealizationParams
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     hp = RealizationParams(q=pin(params.q), cond=pin(params.cond), poro=pin(params.poro), thick=pin(params.thick), coef=pin(params.coef))
-    for _ in range(2):                                       # warm: the work lattice differs from the resident-input leg's,
-        res = eng.run(spec, hp, group=group)                 # so the bitmap workspace is re-allocated on the first call
+    if args.no_e2e:
+        hp = None
+    for _ in range(2 if hp is not None else 0):              # warm: the work lattice differs from the resident-input leg's,
+        res = eng.run(spec, hp, group=group, reuse_lattice=False)   # so the bitmap workspace is re-allocated on the first call
     e2e_steps = max(1, args.steps)
     barrier()
     t0 = time.perf_counter()
     e_att = 0
-    for _ in range(e2e_steps):
-        res = eng.run(spec, hp, group=group)
+    for _ in range(e2e_steps if hp is not None else 0):
+        res = eng.run(spec, hp, group=group, reuse_lattice=False)
         e_att += res["stats"]["attempts"]
     barrier()
     e_s = time.perf_counter() - t0
@@ -337,10 +339,10 @@ def run_ours(args):
         dist.all_reduce(ea, op=dist.ReduceOp.SUM)
     h2d = int(params.q.nbytes + params.cond.nbytes + params.poro.nbytes + params.thick.nbytes + params.coef.nbytes
               + spec.well_xy.nbytes + start.nbytes)
-    d2h = int(res["counts"].nbytes + 10 * 8)
-    e2e = {"value": float(ea.item()) / float(et.item()), "unit": "DOPRI5 attempts/s", "h2d_bytes_per_step": h2d,
+    d2h = int(res["counts"].nbytes + 10 * 8) if hp is not None else 0
+    e2e = None if hp is None else {"value": float(ea.item()) / float(et.item()), "unit": "DOPRI5 attempts/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "realizations_per_s": world * R * e2e_steps / float(et.item()),
-           "api": "Engine.run(spec, params_host) = H2D + guarded capture (+ allreduce) + crop + D2H; lattice estimate reused from the warm-up call", "steps": e2e_steps}
+           "api": "Engine.run(spec, params_host, reuse_lattice=False) = H2D + pilot pass + guarded capture (+ allreduce) + crop + D2H, all inside every timed call", "steps": e2e_steps}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -380,6 +382,7 @@ def main():
     ap.add_argument("--npaths", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20200725)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel A/B runs while tuning)")
     ap.add_argument("--unconfined", action="store_true", help="confined=False: the head-dependent velocity of model.py:353-389")
     args = ap.parse_args()
     if args.impl == "reference":

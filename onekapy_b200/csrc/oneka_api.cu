@@ -72,16 +72,17 @@ __device__ __forceinline__ double cf_F(const TrackParams &tp, long long r) { ret
 
 template <bool CONFINED>
 __device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc,
-                                                  double2 *s_wxy, double *s_w)
+                                                  double *s_wells)
 {
     const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
     const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
-    float *s_w32 = const_cast<float *>(w32_of(s_w, tp.nw));
-    for (int i = threadIdx.x; i < tp.nw; i += blockDim.x) {
-        s_wxy[i] = make_double2(tp.well_xy[2 * i], tp.well_xy[2 * i + 1]);
-        const double w = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;    // q/(2 pi) [/(H n)]
-        s_w[i] = w;
-        if (!CONFINED) s_w32[i] = (float)w;
+    for (int i = threadIdx.x; i < ((tp.nw + 3) & ~3); i += blockDim.x) {            // layout: oneka_device.cuh, WELL_BLK
+        const bool real = i < tp.nw;
+        const double w = real ? tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale : 0.0;    // q/(2 pi) [/(H n)]
+        well_x(s_wells, i) = real ? tp.well_xy[2 * i] : 0.0;
+        well_y(s_wells, i) = real ? tp.well_xy[2 * i + 1] : 0.0;
+        well_w(s_wells, i) = w;
+        well_w32(s_wells, i) = (float)w;
     }
     if (threadIdx.x == 0) {
         const double *cf = tp.coef + 6 * r;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
         // <= nw * 2^-24 * 47 sum|w|; times 0.5 ln 2, with a 5x margin:  2e-5 (nw + 16) sum|w|
         if (threadIdx.x == 0) {
             double sw = 0.0;
-            for (int i = 0; i < tp.nw; ++i) sw += fabs(s_w[i]);
+            for (int i = 0; i < tp.nw; ++i) sw += fabs(well_w(s_wells, i));
             rc.pot_err = 2e-5 * (double)(tp.nw + 16) * sw + 1e-9 * fabs(cf_F(tp, r));
         }
         __syncthreads();
@@ -117,16 +118,15 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
     __shared__ double s_lat[5];
-    double2 *s_wxy = s_dyn;
-    double *s_w = reinterpret_cast<double *>(s_dyn + tp.nw);
+    double *s_wells = reinterpret_cast<double *>(s_dyn);
     if (MODE == 1) stage_lattice(L, s_lat);
 
     const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long r = blockIdx.x / chunks;
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
-    stage_realization<CONFINED>(tp, r, rc, s_wxy, s_w);
+    stage_realization<CONFINED>(tp, r, rc, s_wells);
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wxy, s_w, r, p, p < tp.P);
+    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P);
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per
@@ -195,11 +195,10 @@ eval_points_kernel(TrackParams tp, long long npts, const double *pts, double *ou
 {
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc_c, rc_u;
-    double2 *s_wxy = s_dyn;
-    double *s_wc = reinterpret_cast<double *>(s_dyn + tp.nw);
-    double *s_wu = s_wc + ((tp.nw + 1) & ~1) + (tp.nw + 1) / 2 + 2;      // past s_wc and the (unused) float slot behind it
-    stage_realization<true>(tp, 0, rc_c, s_wxy, s_wc);
-    stage_realization<false>(tp, 0, rc_u, s_wxy, s_wu);
+    double *s_wc = reinterpret_cast<double *>(s_dyn);                    // two well stores: confined and unconfined scaling
+    double *s_wu = s_wc + well_store_doubles(tp.nw);
+    stage_realization<true>(tp, 0, rc_c, s_wc);
+    stage_realization<false>(tp, 0, rc_u, s_wu);
     for (long long i = threadIdx.x; i < npts; i += blockDim.x) {
         const double x = pts[2 * i], y = pts[2 * i + 1];
         double *o = out + 8 * i;
@@ -209,20 +208,20 @@ eval_points_kernel(TrackParams tp, long long npts, const double *pts, double *ou
         double qx = -(rc_u.a2 * dx0 + rc_u.c * dy0 + rc_u.d);           // model.py:303-304
         double qy = -(rc_u.b2 * dy0 + rc_u.c * dx0 + rc_u.e);
         for (int w = 0; w < tp.nw; ++w) {
-            const double dx = x - s_wxy[w].x, dy = y - s_wxy[w].y;
+            const double dx = x - well_x(s_wu, w), dy = y - well_y(s_wu, w), ww = well_w(s_wu, w);
             const double r2 = dx * dx + dy * dy;
-            pot += 0.5 * s_wu[w] * log(r2);
-            qx -= s_wu[w] * dx / r2;                                     // model.py:312-313
-            qy -= s_wu[w] * dy / r2;
+            pot += 0.5 * ww * log(r2);
+            qx -= ww * dx / r2;                                          // model.py:312-313
+            qy -= ww * dy / r2;
         }
         o[0] = pot; o[1] = qx; o[2] = qy;
         double fx, fy;
-        field_feval<true>(rc_c, s_wxy, s_wc, tp.nw, x, y, fx, fy);
+        field_feval<true>(rc_c, s_wc, tp.nw, x, y, fx, fy);
         o[3] = -fx; o[4] = -fy;
         o[5] = o[6] = o[7] = nan("");
         if (pot > 0.0) {
             o[5] = (pot < rc_u.half_kH2) ? sqrt(2.0 * pot / rc_u.k) : (pot + rc_u.half_kH2) / (rc_u.k * rc_u.H);   // model.py:345-349
-            if (field_feval<false>(rc_u, s_wxy, s_wu, tp.nw, x, y, fx, fy) == PATH_OK) { o[6] = -fx; o[7] = -fy; }
+            if (field_feval<false>(rc_u, s_wu, tp.nw, x, y, fx, fy) == PATH_OK) { o[6] = -fx; o[7] = -fy; }
         }
     }
 }
@@ -326,10 +325,8 @@ static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_d
     return tp;
 }
 
-// + 32 B: ptxas widens the scaled-discharge loads of the remainder iterations to LDS.128 (w[i], w[i+1]); with an odd
-// number of wells the second half lies 8 bytes past w[nw-1].  Harmless on hardware, but compute-sanitizer flags it.
-// + nw floats (+ alignment): FP32 copies of the scaled discharges for the unconfined screening sum.
-static size_t track_smem(int nw) { return (size_t)nw * (sizeof(double2) + sizeof(double) + sizeof(float)) + 64; }
+// the well store of oneka_device.cuh (blocks of 4 wells, WELL_BLK doubles each) + 16 bytes of slack
+static size_t track_smem(int nw) { return (size_t)well_store_doubles(nw) * sizeof(double) + 16; }
 
 static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
 {
@@ -580,7 +577,7 @@ int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const doub
         if (!(mm.tol > 0)) mm.tol = 1.0;
         if (!(mm.maxstep > 0)) mm.maxstep = 1.0;
         TrackParams tp = make_track(&mm, d_wxy, 1, 1, d_q, d_k, d_n, d_H, d_cf, nullptr, ctx->stats_dev);
-        const size_t smem = (size_t)nw * (sizeof(double2) + 2 * (sizeof(double) + sizeof(float))) + 160;
+        const size_t smem = 2 * track_smem(nw);
         if (smem > 48 * 1024) TRY2(cudaFuncSetAttribute(eval_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_points_kernel<<<1, 128, smem, s>>>(tp, npts, d_pts, d_out);
         ctx->launches++;

@@ -38,11 +38,20 @@ struct RealConsts {
     double xo, yo;
 };
 
-// the FP32 copies of the scaled discharges live right behind the FP64 ones in shared memory (unconfined only)
-__device__ __forceinline__ const float *w32_of(const double *s_w, int nw)
-{
-    return reinterpret_cast<const float *>(s_w + ((nw + 1) & ~1));
-}
+// Wells in shared memory, blocks of 4 (WELL_BLK doubles = 112 bytes each, 16-byte aligned):
+//   [0..7]  x0 y0 x1 y1 x2 y2 x3 y3      [8..11]  w0 w1 w2 w3 (scaled discharges)      [12..13]  the same w as 4 floats
+// One uniform base register addresses a whole block with immediate offsets (6 LDS.128 per 4 wells, 3 uniform
+// instructions of loop control); the last block may be partial (its unused slots are zero and never read by the
+// hot loop, which finishes with single wells).
+constexpr int WELL_BLK = 14;
+__host__ __device__ __forceinline__ constexpr int well_store_doubles(int nw) { return ((nw + 3) >> 2) * WELL_BLK; }
+__device__ __forceinline__ double &well_x(double *s, int i) { return s[(i >> 2) * WELL_BLK + 2 * (i & 3)]; }
+__device__ __forceinline__ double &well_y(double *s, int i) { return s[(i >> 2) * WELL_BLK + 2 * (i & 3) + 1]; }
+__device__ __forceinline__ double &well_w(double *s, int i) { return s[(i >> 2) * WELL_BLK + 8 + (i & 3)]; }
+__device__ __forceinline__ float &well_w32(double *s, int i) { return reinterpret_cast<float *>(s + (i >> 2) * WELL_BLK + 12)[i & 3]; }
+__device__ __forceinline__ double well_x(const double *s, int i) { return s[(i >> 2) * WELL_BLK + 2 * (i & 3)]; }
+__device__ __forceinline__ double well_y(const double *s, int i) { return s[(i >> 2) * WELL_BLK + 2 * (i & 3) + 1]; }
+__device__ __forceinline__ double well_w(const double *s, int i) { return s[(i >> 2) * WELL_BLK + 8 + (i & 3)]; }
 
 struct TrackParams {
     int nw;
@@ -122,14 +131,25 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 //   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
 //   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
 //   reference's AquiferError -> PATH_AQUIFER_DRY.
-#ifndef ONEKA_WELL_UNROLL
-#define ONEKA_WELL_UNROLL 4
-#endif
-constexpr int WELL_UNROLL = ONEKA_WELL_UNROLL;
+// one well's term of the sum: 9 FP64-pipe instructions + MUFU.RCP64H
+template <bool CONFINED>
+__device__ __forceinline__ void well_term(double x, double y, double xw, double yw, double w, float w32,
+                                          double &gx, double &gy, float &lsum32)
+{
+    const double dx = x - xw;
+    const double dy = y - yw;
+    const double r2 = fma(dy, dy, dx * dx);
+    double y0, t;
+    rcp_parts(r2, y0, t);
+    const double s0 = w * y0;
+    const double s = fma(s0, t, s0);
+    gx = fma(s, dx, gx);
+    gy = fma(s, dy, gy);
+    if (!CONFINED) lsum32 = fmaf(w32, __log2f((float)r2), lsum32);
+}
 
 template <bool CONFINED>
-__device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *__restrict__ s_wxy,
-                                           const double *__restrict__ s_w, int nw,
+__device__ __forceinline__ int field_feval(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
                                            double x, double y, double &fx, double &fy)
 {
     const double dx0 = x - rc.xo;
@@ -138,22 +158,39 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
     // unconfined: FP32 screening sum of  w_i log2(r_i^2)  (MUFU.LG2 on the XU pipe; the exact FP64 logs below are
     // needed only where the aquifer is not fully saturated)
-    const float *s_w32 = CONFINED ? nullptr : w32_of(s_w, nw);
     float lsum32 = 0.0f;
-#pragma unroll WELL_UNROLL
-    for (int i = 0; i < nw; ++i) {
-        const double2 wxy = s_wxy[i];
-        const double w = s_w[i];
-        const double dx = x - wxy.x;
-        const double dy = y - wxy.y;
-        const double r2 = fma(dy, dy, dx * dx);
-        double y0, t;
-        rcp_parts(r2, y0, t);
-        const double s0 = w * y0;
-        const double s = fma(s0, t, s0);
-        gx = fma(s, dx, gx);
-        gy = fma(s, dy, gy);
-        if (!CONFINED) lsum32 = fmaf(s_w32[i], __log2f((float)r2), lsum32);
+    const double *p = s_wells;
+    const double *const pend = s_wells + (nw >> 2) * WELL_BLK;
+#pragma unroll 1
+    for (; p != pend; p += WELL_BLK) {
+        const double2 c0 = reinterpret_cast<const double2 *>(p)[0];
+        const double2 c1 = reinterpret_cast<const double2 *>(p)[1];
+        const double2 c2 = reinterpret_cast<const double2 *>(p)[2];
+        const double2 c3 = reinterpret_cast<const double2 *>(p)[3];
+        const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
+        const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
+        float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
+        well_term<CONFINED>(x, y, c0.x, c0.y, w01.x, wf.x, gx, gy, lsum32);
+        well_term<CONFINED>(x, y, c1.x, c1.y, w01.y, wf.y, gx, gy, lsum32);
+        well_term<CONFINED>(x, y, c2.x, c2.y, w23.x, wf.z, gx, gy, lsum32);
+        well_term<CONFINED>(x, y, c3.x, c3.y, w23.y, wf.w, gx, gy, lsum32);
+    }
+    {   // the last, partial block: single wells
+        const int rem = nw & 3;
+        const float *pf = reinterpret_cast<const float *>(p + 12);
+        if (rem > 0) {
+            const double2 c = reinterpret_cast<const double2 *>(p)[0];
+            well_term<CONFINED>(x, y, c.x, c.y, p[8], CONFINED ? 0.f : pf[0], gx, gy, lsum32);
+        }
+        if (rem > 1) {
+            const double2 c = reinterpret_cast<const double2 *>(p)[1];
+            well_term<CONFINED>(x, y, c.x, c.y, p[9], CONFINED ? 0.f : pf[1], gx, gy, lsum32);
+        }
+        if (rem > 2) {
+            const double2 c = reinterpret_cast<const double2 *>(p)[2];
+            well_term<CONFINED>(x, y, c.x, c.y, p[10], CONFINED ? 0.f : pf[2], gx, gy, lsum32);
+        }
     }
     if (CONFINED) {
         fx = gx;
@@ -174,10 +211,9 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double2 *
         // not (certainly) saturated: the reference's potential with FP64 logs (model.py:259-266)
         double lsum = 0.0;
         for (int i = 0; i < nw; ++i) {
-            const double2 wxy = s_wxy[i];
-            const double dx = x - wxy.x;
-            const double dy = y - wxy.y;
-            lsum = fma(s_w[i], log(fma(dy, dy, dx * dx)), lsum);
+            const double dx = x - well_x(s_wells, i);
+            const double dy = y - well_y(s_wells, i);
+            lsum = fma(well_w(s_wells, i), log(fma(dy, dy, dx * dx)), lsum);
         }
         const double pot = fma(0.5, lsum, pot_reg);                     // 0.5*lsum = sum q ln(r2)/(4 pi) since w = q/(2 pi)
         if (!(pot > 0.0)) return PATH_AQUIFER_DRY;                      // model.py:343-344 (nan also ends the trace)
@@ -454,7 +490,7 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
 template <bool CONFINED, int MODE>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
-                                            const RealConsts &rc, const double2 *s_wxy, const double *s_w,
+                                            const RealConsts &rc, const double *s_wells,
                                             long long r, int p, bool active)
 {
     // Dormand-Prince tableau, capturezone.py:202-209
@@ -496,7 +532,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
             vout = tp.verts + ((size_t)r * tp.P + p) * (size_t)tp.max_verts * 2;
             if (tp.max_verts > 0) { vout[0] = x; vout[1] = y; }
         }
-        status = field_feval<CONFINED>(rc, s_wxy, s_w, nw, x, y, k1x, k1y);   // :219
+        status = field_feval<CONFINED>(rc, s_wells, nw, x, y, k1x, k1y);   // :219
         if (status != PATH_OK) running = false;
     }
 
@@ -518,26 +554,26 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
                                            fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                  // :228
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
                                            fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                   // :229
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                st = field_feval<CONFINED>(rc, s_wells, nw,
                                            fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
                                            fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);    // :230
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw,
+                st = field_feval<CONFINED>(rc, s_wells, nw,
                                            fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
                                            fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);         // :233
                 const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
-                st = field_feval<CONFINED>(rc, s_wxy, s_w, nw, xt, yt, k7x, k7y);                                            // :236
+                st = field_feval<CONFINED>(rc, s_wells, nw, xt, yt, k7x, k7y);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238
