@@ -11,6 +11,8 @@
 #include <cstring>
 #include <vector>
 #include <new>
+#include <mutex>
+#include <cstdlib>
 
 using namespace oneka;
 
@@ -63,7 +65,29 @@ struct oneka_ctx {
     std::vector<EvPair> events;
     double track_ms = 0.0, flush_ms = 0.0;
     uint64_t track_launches = 0;
+    int cslot = -1;                         // this context's slot of c_wellxy, or -1 (shared-memory well coordinates)
 };
+
+// slots of c_wellxy in use, per device (bit i = slot i); contexts beyond CONST_SLOTS keep the coordinates in shared memory
+static std::mutex g_slot_mu;
+static unsigned int g_slots_used[64] = {0};
+
+static int acquire_cslot(int device)
+{
+    const char *off = getenv("ONEKA_B200_NO_CONST_WELLS");          // A/B switch: shared-memory well coordinates
+    if ((off && off[0] == '1') || device < 0 || device >= 64) return -1;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (int i = 0; i < CONST_SLOTS; ++i)
+        if (!(g_slots_used[device] & (1u << i))) { g_slots_used[device] |= 1u << i; return i; }
+    return -1;
+}
+
+static void release_cslot(int device, int slot)
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    g_slots_used[device] &= ~(1u << slot);
+}
 
 // ------------------------------------------------------------------------------------------
 // Kernels
@@ -111,9 +135,8 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
 }
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
-template <bool CONFINED, int MODE>
-__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
-track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
+template <bool CONFINED, int MODE, bool WPARAM>
+__device__ __forceinline__ void track_body(const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps, const WellXY *wxy)
 {
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
@@ -126,7 +149,22 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
     stage_realization<CONFINED>(tp, r, rc, s_wells);
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P);
+    dopri_track<CONFINED, MODE, WPARAM>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, wxy);
+}
+
+template <bool CONFINED, int MODE>
+__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
+track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
+{
+    track_body<CONFINED, MODE, false>(tp, L, bitmaps, nullptr);
+}
+
+// same, with the well coordinates read from constant-memory slot `cslot` (nw <= CONST_WELLS)
+template <bool CONFINED, int MODE>
+__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
+track_kernel_cw(TrackParams tp, LatticeDev L, unsigned int *bitmaps, int cslot)
+{
+    track_body<CONFINED, MODE, true>(tp, L, bitmaps, &c_wellxy[cslot]);
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per
@@ -362,6 +400,18 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
     const size_t smem = track_smem(tp.nw);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
+    if (ctx->cslot >= 0 && tp.nw > 0 && tp.nw <= CONST_WELLS) {
+        // well coordinates -> this context's constant slot (device to device, stream-ordered: no host round trip)
+        CUDA_TRY(cudaMemcpyToSymbolAsync(c_wellxy, tp.well_xy, (size_t)tp.nw * 2 * sizeof(double),
+                                         (size_t)ctx->cslot * sizeof(WellXY), cudaMemcpyDeviceToDevice, ctx->stream));
+        prof_begin(ctx, 0);
+        if (m->confined) track_kernel_cw<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
+        else track_kernel_cw<false, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
+        prof_end(ctx);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ONEKA_OK;
+    }
     prof_begin(ctx, 0);
     if (m->confined) {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -455,6 +505,7 @@ oneka_ctx *oneka_create(int device)
     }
     if (reset_stats_async(ctx) != ONEKA_OK) { cudaFree(ctx->stats_dev); delete ctx; return nullptr; }
     cudaStreamSynchronize(ctx->stream);
+    ctx->cslot = acquire_cslot(device);
     g_err[0] = 0;
     return ctx;
 }
@@ -468,6 +519,7 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->bitmaps) cudaFree(ctx->bitmaps);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->stats_dev) cudaFree(ctx->stats_dev);
+    release_cslot(ctx->device, ctx->cslot);
     delete ctx;
 }
 

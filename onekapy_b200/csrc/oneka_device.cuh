@@ -131,6 +131,16 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 //   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
 //   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
 //   reference's AquiferError -> PATH_AQUIFER_DRY.
+// Well coordinates are the same for every realization: up to CONST_WELLS of them are copied (device to device, on
+// the context's stream) into a slot of constant memory, from where the hot loop reads them through the UNIFORM
+// datapath (LDCU into uniform registers that the FP64 instructions take as operands) instead of one LDS.128 per
+// well on the vector issue port.  One slot per context (CONST_SLOTS per device and process; later contexts and
+// larger fields use the shared-memory copy).
+constexpr int CONST_WELLS = 256;
+constexpr int CONST_SLOTS = 12;
+struct __align__(16) WellXY { double xy[2 * CONST_WELLS + 8]; };
+__constant__ WellXY c_wellxy[CONST_SLOTS];
+
 // one well's term of the sum: 9 FP64-pipe instructions + MUFU.RCP64H
 template <bool CONFINED>
 __device__ __forceinline__ void well_term(double x, double y, double xw, double yw, double w, float w32,
@@ -148,9 +158,9 @@ __device__ __forceinline__ void well_term(double x, double y, double xw, double 
     if (!CONFINED) lsum32 = fmaf(w32, __log2f((float)r2), lsum32);
 }
 
-template <bool CONFINED>
+template <bool CONFINED, bool WPARAM = false>
 __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
-                                           double x, double y, double &fx, double &fy)
+                                           double x, double y, double &fx, double &fy, const WellXY *wxy = nullptr)
 {
     const double dx0 = x - rc.xo;
     const double dy0 = y - rc.yo;
@@ -160,21 +170,43 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
     // needed only where the aquifer is not fully saturated)
     float lsum32 = 0.0f;
     const double *p = s_wells;
-    const double *const pend = s_wells + (nw >> 2) * WELL_BLK;
+    if (WPARAM) {
+        const int nb = nw >> 2;
+        // coordinates of the NEXT block are fetched (uniform loads) while the current one is computed; the slot is
+        // padded by one block, so the read past the last full block is in bounds
+        const double *c = wxy->xy;
+        double n0 = c[0], n1 = c[1], n2 = c[2], n3 = c[3], n4 = c[4], n5 = c[5], n6 = c[6], n7 = c[7];
 #pragma unroll 1
-    for (; p != pend; p += WELL_BLK) {
-        const double2 c0 = reinterpret_cast<const double2 *>(p)[0];
-        const double2 c1 = reinterpret_cast<const double2 *>(p)[1];
-        const double2 c2 = reinterpret_cast<const double2 *>(p)[2];
-        const double2 c3 = reinterpret_cast<const double2 *>(p)[3];
-        const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
-        const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
-        float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
-        well_term<CONFINED>(x, y, c0.x, c0.y, w01.x, wf.x, gx, gy, lsum32);
-        well_term<CONFINED>(x, y, c1.x, c1.y, w01.y, wf.y, gx, gy, lsum32);
-        well_term<CONFINED>(x, y, c2.x, c2.y, w23.x, wf.z, gx, gy, lsum32);
-        well_term<CONFINED>(x, y, c3.x, c3.y, w23.y, wf.w, gx, gy, lsum32);
+        for (int b = 0; b < nb; ++b, p += WELL_BLK) {
+            const double x0 = n0, y0 = n1, x1 = n2, y1 = n3, x2 = n4, y2 = n5, x3 = n6, y3 = n7;
+            c += 8;
+            n0 = c[0]; n1 = c[1]; n2 = c[2]; n3 = c[3]; n4 = c[4]; n5 = c[5]; n6 = c[6]; n7 = c[7];
+            const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
+            const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
+            float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
+            well_term<CONFINED>(x, y, x0, y0, w01.x, wf.x, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, x1, y1, w01.y, wf.y, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, x2, y2, w23.x, wf.z, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, x3, y3, w23.y, wf.w, gx, gy, lsum32);
+        }
+    } else {
+        const double *const pend = s_wells + (nw >> 2) * WELL_BLK;
+#pragma unroll 1
+        for (; p != pend; p += WELL_BLK) {
+            const double2 c0 = reinterpret_cast<const double2 *>(p)[0];
+            const double2 c1 = reinterpret_cast<const double2 *>(p)[1];
+            const double2 c2 = reinterpret_cast<const double2 *>(p)[2];
+            const double2 c3 = reinterpret_cast<const double2 *>(p)[3];
+            const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
+            const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
+            float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
+            well_term<CONFINED>(x, y, c0.x, c0.y, w01.x, wf.x, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, c1.x, c1.y, w01.y, wf.y, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, c2.x, c2.y, w23.x, wf.z, gx, gy, lsum32);
+            well_term<CONFINED>(x, y, c3.x, c3.y, w23.y, wf.w, gx, gy, lsum32);
+        }
     }
     {   // the last, partial block: single wells
         const int rem = nw & 3;
@@ -488,10 +520,10 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // ------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
-template <bool CONFINED, int MODE>
+template <bool CONFINED, int MODE, bool WPARAM = false>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
-                                            long long r, int p, bool active)
+                                            long long r, int p, bool active, const WellXY *wxy = nullptr)
 {
     // Dormand-Prince tableau, capturezone.py:202-209
     constexpr double a20 = 1.0 / 5.0;
@@ -532,7 +564,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
             vout = tp.verts + ((size_t)r * tp.P + p) * (size_t)tp.max_verts * 2;
             if (tp.max_verts > 0) { vout[0] = x; vout[1] = y; }
         }
-        status = field_feval<CONFINED>(rc, s_wells, nw, x, y, k1x, k1y);   // :219
+        status = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, x, y, k1x, k1y, wxy);   // :219
         if (status != PATH_OK) running = false;
     }
 
@@ -554,26 +586,26 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y, wxy);      // :227
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
-                                           fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                  // :228
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                                           fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y, wxy);                                  // :228
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
-                                           fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                   // :229
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                                           fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y, wxy);                   // :229
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw,
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw,
                                            fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
-                                           fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);    // :230
+                                           fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y, wxy);    // :230
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw,
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw,
                                            fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
-                                           fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
+                                           fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y, wxy);  // :231
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);         // :233
                 const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
-                st = field_feval<CONFINED>(rc, s_wells, nw, xt, yt, k7x, k7y);                                            // :236
+                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, xt, yt, k7x, k7y, wxy);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238

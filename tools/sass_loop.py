@@ -22,6 +22,7 @@ def cls(t):
     op = t.split()[0] if not t.startswith("@") else t.split()[1]
     if op.startswith(("DFMA", "DADD", "DMUL", "DSETP", "DMNMX")): return "fp64"
     if op.startswith("MUFU"): return "mufu"
+    if op.startswith("LDCU"): return "ctl/uniform"
     if op.startswith(("LDS", "STS", "LDG", "STG", "LDL", "STL", "RED", "ATOM", "LDC")): return "mem"
     if op.startswith(("U", "S2UR", "R2UR", "BRA", "BSSY", "BSYNC")): return "ctl/uniform"
     if op.startswith(("MOV", "IMAD.MOV")): return "mov"
