@@ -342,6 +342,10 @@ static int make_lattice(const oneka_lattice *lat, LatticeDev &L)
     L.umbra32 = (float)lat->umbra; L.inv_dx32 = 1.0f / L.dx32;
     L.maxd = lat->deltax > lat->deltay ? lat->deltax : lat->deltay;
     L.inv_dx = 1.0 / lat->deltax; L.inv_dy = 1.0 / lat->deltay;
+    L.cxl = lat->xmin + lat->umbra; L.cxr = lat->xmin - lat->umbra;
+    L.cyb = lat->ymin + lat->umbra; L.cyt = lat->ymin - lat->umbra;
+    L.s16x = 65536.0 / lat->deltax; L.s16y = 65536.0 / lat->deltay;
+    L.fixed_ok = (lat->nrows < 30000 && lat->ncols < 30000) ? 1 : 0;
     L.words = (unsigned long long)L.nrows * (unsigned long long)L.wpr;
     return ONEKA_OK;
 }

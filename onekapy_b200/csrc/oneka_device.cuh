@@ -85,6 +85,11 @@ struct LatticeDev {
     float dx32, dy32, umbra2_32, umbra32, inv_dx32;
     double maxd;                     // max(dx, dy)
     double inv_dx, inv_dy;           // 1/dx, 1/dy (window pre-quotient, see floor_div)
+    // fixed-point window (raster_seg): cell index * 2^16 = (coordinate - c??) * s16?;  fixed_ok when the lattice is
+    // small enough for that to fit an int32 with room to saturate
+    double cxl, cxr, cyb, cyt;       // xmin + umbra, xmin - umbra, ymin + umbra, ymin - umbra
+    double s16x, s16y;               // 65536/dx, 65536/dy
+    int fixed_ok;
     unsigned long long words;        // words per bitmap = nrows*wpr
 };
 
@@ -356,17 +361,33 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
                                            const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr)
 {
     // ---- window, probabilityfield.py:298-301 ----
+    // left = floor((min(ax,bx) - umbra - xmin)/dx) etc.  Fast path: the four quotients in 16.16 fixed point from one
+    // subtraction and one multiplication each (a few ulps away from the reference's sub, sub, div); a quotient within
+    // 3 * 2^-16 of an integer -- where those ulps could change the floor -- sends the segment to the exact path
+    // (floor_div: the reference's own operations).
     const double mnx = (bx < ax) ? bx : ax, mxx = (bx > ax) ? bx : ax;
     const double mny = (by < ay) ? by : ay, mxy = (by > ay) ? by : ay;
-    const double fl = floor_div(__dsub_rn(mnx, L.umbra), L.xmin, L.dx, L.inv_dx);
-    const double fr = floor_div(__dadd_rn(mxx, L.umbra), L.xmin, L.dx, L.inv_dx);
-    const double fb = floor_div(__dsub_rn(mny, L.umbra), L.ymin, L.dy, L.inv_dy);
-    const double ft = floor_div(__dadd_rn(mxy, L.umbra), L.ymin, L.dy, L.inv_dy);
-    const double lo_x = fmax(fl, (double)cw.l), hi_x = fmin(fr + 1.0, (double)cw.r);
-    const double lo_y = fmax(fb, (double)cw.b), hi_y = fmin(ft + 1.0, (double)cw.t);
-    if (fl < (double)cw.l || fb < (double)cw.b || fr + 1.0 > (double)cw.r || ft + 1.0 > (double)cw.t) ctr.clipped++;
-    if (!(lo_x < hi_x) || !(lo_y < hi_y)) return;                        // empty window (also nan)
-    const int left = (int)lo_x, right = (int)hi_x, bottom = (int)lo_y, top = (int)hi_y;
+    int fl, fr, fb, ft;
+    bool fast = L.fixed_ok != 0;
+    if (fast) {
+        const int ql = __double2int_rd((mnx - L.cxl) * L.s16x), qr = __double2int_rd((mxx - L.cxr) * L.s16x);
+        const int qb = __double2int_rd((mny - L.cyb) * L.s16y), qt = __double2int_rd((mxy - L.cyt) * L.s16y);
+        constexpr unsigned int T = 3u;                                   // saturated conversions stay far outside the lattice
+        const bool amb = (((unsigned int)ql + T) & 0xffffu) <= 2u * T || (((unsigned int)qr + T) & 0xffffu) <= 2u * T ||
+                         (((unsigned int)qb + T) & 0xffffu) <= 2u * T || (((unsigned int)qt + T) & 0xffffu) <= 2u * T;
+        fl = ql >> 16; fr = qr >> 16; fb = qb >> 16; ft = qt >> 16;
+        fast = !amb;
+    }
+    if (!fast) {
+        constexpr double BIG = 1073741824.0;                             // 2^30: keeps fr + 1 inside an int
+        fl = (int)fmax(-BIG, fmin(BIG, floor_div(__dsub_rn(mnx, L.umbra), L.xmin, L.dx, L.inv_dx)));
+        fr = (int)fmax(-BIG, fmin(BIG, floor_div(__dadd_rn(mxx, L.umbra), L.xmin, L.dx, L.inv_dx)));
+        fb = (int)fmax(-BIG, fmin(BIG, floor_div(__dsub_rn(mny, L.umbra), L.ymin, L.dy, L.inv_dy)));
+        ft = (int)fmax(-BIG, fmin(BIG, floor_div(__dadd_rn(mxy, L.umbra), L.ymin, L.dy, L.inv_dy)));
+    }
+    const int left = max(fl, cw.l), right = min(fr + 1, cw.r), bottom = max(fb, cw.b), top = min(ft + 1, cw.t);
+    if (fl < cw.l || fb < cw.b || fr + 1 > cw.r || ft + 1 > cw.t) ctr.clipped++;
+    if (left >= right || bottom >= top) return;                          // empty window
 
     const double bax = __dsub_rn(bx, ax), bay = __dsub_rn(by, ay);
     const double len2 = __dadd_rn(__dmul_rn(bax, bax), __dmul_rn(bay, bay));
@@ -414,11 +435,19 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     const float cr = fmaf(kk, m, uy);
     const float kisy = kk * isy;
     const float ylo = fminf(0.0f, fbay), yhi = fmaxf(0.0f, fbay);
-    const float tau = fmaxf(1e-3f * u, 256.0f * EPS32 * Lm);
+#ifndef ONEKA_TAU_REL
+#define ONEKA_TAU_REL 1e-3f
+#endif
+    const float tau = fmaxf(ONEKA_TAU_REL * u, 256.0f * EPS32 * Lm);
     const float k_edge = 4.0f * EPS32 * Lm * fmaf(17.0f, fabsf(m), 11.0f) * L.inv_dx32;     // [cells]
     const float k_cap = 40.0f * EPS32 * Lm * Lm * L.inv_dx32;                                // [cells * m]
     const int ncol = right - left;
-    const bool scan_ok = !all_exact && ncol >= ONEKA_SCAN_MIN_COLS && (fabsf(fbay) * 64.0f > fabsf(fbax)) && u > 0.0f;
+    // A straight-edge end is trusted only while its error bound stays well below one cell (k_edge grows with the slope
+    // |m| = |sx/sy|); on near-horizontal segments almost every row ends on the two caps, whose bounds do not involve m,
+    // so only the rows that do cross a straight edge fall back to the node loop (edge_ok false; also for sy = 0, where
+    // m and k_edge are inf or nan).
+    const bool edge_ok = k_edge < 0.125f;
+    const bool scan_ok = !all_exact && ncol >= ONEKA_SCAN_MIN_COLS && u > 0.0f;
 
     unsigned int *row = bm + (size_t)bottom * L.wpr;
     float fi = 0.0f;
@@ -435,7 +464,8 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
             const bool ra = tr < 0.0f, rb = tr > 1.0f, la = tl < 0.0f, lb = tl > 1.0f;
             const float xr = ra ? ha : (rb ? fbax + hb : fmaf(m, cay, cr));
             const float xl = la ? -ha : (lb ? fbax - hb : fmaf(m, cay, -cr));
-            if (xr > xl) {                                               // also false for nan
+            const bool caps_only = (la | lb) & (ra | rb);
+            if (xr > xl && (edge_ok | caps_only)) {                      // also false for nan
                 const float fl = (xl - base_x) * L.inv_dx32, fr = (xr - base_x) * L.inv_dx32;
                 // round-to-nearest and float->int through the 1.5 * 2^23 trick (FMA-pipe adds instead of the
                 // quarter-rate FRND / F2I of the XU pipe); exact for |f| < 2^22, the window is far smaller

@@ -228,6 +228,47 @@ def test_raster_scanline_configs_vs_oracle(eng, dx, dy, umbra, step, snap):
     assert ndiff == 0
 
 
+@pytest.mark.parametrize("dx,dy,umbra", [(4.0, 4.0, 8.0), (1.0, 1.0, 7.5), (3.0, 0.5, 2.0)])
+def test_raster_flat_segments_vs_oracle(eng, dx, dy, umbra):
+    """Near-horizontal segments of every flatness (slope 0 ... 1/20, both signs, both directions), with the capsule's
+    tangent lines placed on, just above and just below lattice rows: the rows that end on the two caps take the
+    scan-line path whatever the slope, the rows that cross a straight edge of a flat segment take the node loop."""
+    from onekapy_b200.lattice import LatticeGeom
+    from oracle import oracle as O
+    rng = np.random.default_rng(int(97 * dx + 13 * umbra))
+    slopes = [0.0, 1e-15, 1e-12, 1e-9, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 3e-3, 1e-2, 1.0 / 64, 1.0 / 63, 0.03, 0.05]
+    offs = [0.0, 1e-13, -1e-13, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4, 2e-3, -2e-3, 0.3]
+    tracks = []
+    for k in range(900):
+        n = int(rng.integers(2, 12))
+        sl = slopes[k % len(slopes)] * rng.choice([-1.0, 1.0])
+        sx = rng.uniform(0.5, 15.0, size=n) * rng.choice([-1.0, 1.0])
+        steps = np.stack([sx, sx * sl], axis=1)
+        row = 100.0 + dy * int(rng.integers(-8, 8))                     # a lattice row (anchor 100 - dy, spacing dy)
+        y0 = row + rng.choice([-umbra, umbra, 0.0]) + offs[k % len(offs)]   # tangent line on / next to that row
+        v = np.cumsum(steps, axis=0) + np.array([rng.uniform(70, 130), 0.0])
+        v[:, 1] += y0 - v[0, 1]
+        tracks.append(v)
+    gm = LatticeGeom.anchored(dx, dy, 100.0, 100.0).expanded(20.0, 180.0, 40.0, 160.0)
+    real_of = (np.arange(len(tracks)) % 3).astype(np.int32)
+    eng.reset_stats()
+    counts = eng.raster_traces(gm, umbra, tracks, real_of, 3)
+    st = eng.read_stats()
+    of = O.Field(dx, dy, 100.0, 100.0)
+    of.expand(20.0, 180.0, 40.0, 160.0)
+    for r in range(3):
+        for t, rr in zip(tracks, real_of):
+            if rr == r:
+                for i in range(len(t) - 1):
+                    of.insert(t[i, 0], t[i, 1], t[i + 1, 0], t[i + 1, 1], umbra)
+        of.register(1.0)
+    ref = of.pgrid.astype(np.uint32)
+    ndiff = np.count_nonzero(counts != ref)
+    print("flat segments dx %.1f dy %.1f umbra %.1f: %d segments, %d exact re-tests, differing cells %d of %d"
+          % (dx, dy, umbra, st["steps"], st["exact_tests"], ndiff, np.count_nonzero(ref)))
+    assert ndiff == 0
+
+
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CAPTURES)
 def test_traces_vs_reference(eng, golden, name):
