@@ -167,10 +167,13 @@ track_kernel_cw(TrackParams tp, LatticeDev L, unsigned int *bitmaps, int cslot)
     track_body<CONFINED, MODE, true>(tp, L, bitmaps, &c_wellxy[cslot]);
 }
 
-// register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per
-// bitmap word position, looping over its slice of realization slots; per-bit counters live
-// in registers, bitmap words are zeroed as they are consumed, counts get one RED per nonzero
-// counter.  Reads are coalesced (consecutive threads = consecutive words of one slot).
+// register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per bitmap word position,
+// looping over its slice of realization slots.  HBM-bound (every word of every slot is read once), so the loop keeps
+// FLUSH_UNROLL independent streaming loads in flight per thread (32 B; one load at a time reached ~1 TB/s).  Reads are
+// coalesced (consecutive threads = consecutive words of one slot); per-bit counters live in registers, bitmap words
+// are zeroed as they are consumed, counts get one RED per nonzero counter.
+constexpr int FLUSH_UNROLL = 8;
+
 __global__ void __launch_bounds__(256)
 flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, LatticeDev L, unsigned int *counts,
              const unsigned int *slot_flags)
@@ -183,16 +186,30 @@ flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, Lat
 #pragma unroll
     for (int b = 0; b < 32; ++b) cnt[b] = 0;
     bool any = false;
-    for (long long s = s0; s < s1; ++s) {
-        unsigned int *pw = bitmaps + (size_t)s * L.words + w;
-        const unsigned int v = *pw;
-        if (v) {
-            *pw = 0u;
-            if (slot_flags != nullptr && slot_flags[s]) continue;    // guarded mode: a clipped realization is not registered
-            any = true;
+    auto consume = [&](unsigned int *pw, unsigned int v, long long s) {
+        *pw = 0u;
+        if (slot_flags != nullptr && slot_flags[s]) return;          // guarded mode: a clipped realization is not registered
+        any = true;
 #pragma unroll
-            for (int b = 0; b < 32; ++b) cnt[b] += (v >> b) & 1u;
-        }
+        for (int b = 0; b < 32; ++b) cnt[b] += (v >> b) & 1u;
+    };
+    long long s = s0;
+    unsigned int *pw = bitmaps + (size_t)s0 * L.words + w;
+    for (; s + FLUSH_UNROLL <= s1; s += FLUSH_UNROLL, pw += (size_t)FLUSH_UNROLL * L.words) {
+        unsigned int v[FLUSH_UNROLL];
+#pragma unroll
+        for (int k = 0; k < FLUSH_UNROLL; ++k) v[k] = __ldcs(pw + (size_t)k * L.words);
+        unsigned int acc = 0u;
+#pragma unroll
+        for (int k = 0; k < FLUSH_UNROLL; ++k) acc |= v[k];
+        if (acc == 0u) continue;                                     // most of a bitmap is empty
+#pragma unroll
+        for (int k = 0; k < FLUSH_UNROLL; ++k)
+            if (v[k]) consume(pw + (size_t)k * L.words, v[k], s + k);
+    }
+    for (; s < s1; ++s, pw += L.words) {
+        const unsigned int v = __ldcs(pw);
+        if (v) consume(pw, v, s);
     }
     if (!any) return;
     const int i = (int)(w / L.wpr);

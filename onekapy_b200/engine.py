@@ -395,9 +395,9 @@ class Engine:
             total = parallel.sum_int(R, group, self.device)
         else:
             total = R
-        out = counts.cpu().numpy().view(np.uint32)
+        out = _to_host(counts).view(np.uint32)
         if per_path:
-            pp = {k: v.cpu().numpy() for k, v in pp.items()}
+            pp = {k: _to_host(v) for k, v in pp.items()}
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=final)
 
     # -- the hot path, host buffers in / host grid out (what the drop-in layer calls) -------------
@@ -513,12 +513,25 @@ class Engine:
             total = R
         final = final_geometry(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget, true_bbox)
         i0, j0 = geom.offset_of(final)
-        out = counts[i0:i0 + final.nrows, j0:j0 + final.ncols].contiguous().cpu().numpy().view(np.uint32)
+        out = _to_host(counts[i0:i0 + final.nrows, j0:j0 + final.ncols]).view(np.uint32)
         if per_path:
-            pp = {k: v.cpu().numpy() for k, v in pp.items()}
+            pp = {k: _to_host(v) for k, v in pp.items()}
         if reuse_lattice and not rerun:
             self._geom_hint[key] = work_geom             # it fitted every realization: a good estimate for the next call
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
+
+
+def _to_host(t):
+    """Device tensor -> NumPy array through pinned host memory (torch's caching host allocator): a pageable
+    `.cpu()` copy of an 80 MB count grid ran at 2 GB/s, a third of a C5 step.  The array owns its buffer."""
+    import torch
+    t = t.contiguous()
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def _copy_overlap(src, src_geom, dst, dst_geom):
