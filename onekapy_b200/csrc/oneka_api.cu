@@ -421,13 +421,14 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
     const size_t smem = track_smem(tp.nw);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
-    if (ctx->cslot >= 0 && tp.nw > 0 && tp.nw <= CONST_WELLS) {
+    // (confined only: in the unconfined kernel ptxas does not keep the loop in uniform registers, the constant loads
+    //  become per-thread LDC.64 -- 8 per block against 4 LDS.128 -- and the shared-memory copy is the cheaper one)
+    if (ctx->cslot >= 0 && tp.nw > 0 && tp.nw <= CONST_WELLS && m->confined) {
         // well coordinates -> this context's constant slot (device to device, stream-ordered: no host round trip)
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_wellxy, tp.well_xy, (size_t)tp.nw * 2 * sizeof(double),
                                          (size_t)ctx->cslot * sizeof(WellXY), cudaMemcpyDeviceToDevice, ctx->stream));
         prof_begin(ctx, 0);
-        if (m->confined) track_kernel_cw<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
-        else track_kernel_cw<false, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
+        track_kernel_cw<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
         prof_end(ctx);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());

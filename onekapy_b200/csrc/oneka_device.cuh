@@ -160,7 +160,13 @@ __device__ __forceinline__ void well_term(double x, double y, double xw, double 
     const double s = fma(s0, t, s0);
     gx = fma(s, dx, gx);
     gy = fma(s, dy, gy);
-    if (!CONFINED) lsum32 = fmaf(w32, __log2f((float)r2), lsum32);
+    if (!CONFINED) {
+        // bare MUFU.LG2 (no denormal scaling: (float) r2 is a normal number for 1e-19 m < r < 1e19 m; outside, the
+        // screening value is inf or nan and the comparison in field_feval sends a pumping well's neighbourhood to the FP64 path)
+        float l2;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((float)r2));
+        lsum32 = fmaf(w32, l2, lsum32);
+    }
 }
 
 template <bool CONFINED, bool WPARAM = false>
