@@ -11,8 +11,6 @@
 #include <cstring>
 #include <vector>
 #include <new>
-#include <mutex>
-#include <cstdlib>
 
 using namespace oneka;
 
@@ -65,29 +63,7 @@ struct oneka_ctx {
     std::vector<EvPair> events;
     double track_ms = 0.0, flush_ms = 0.0;
     uint64_t track_launches = 0;
-    int cslot = -1;                         // this context's slot of c_wellxy, or -1 (shared-memory well coordinates)
 };
-
-// slots of c_wellxy in use, per device (bit i = slot i); contexts beyond CONST_SLOTS keep the coordinates in shared memory
-static std::mutex g_slot_mu;
-static unsigned int g_slots_used[64] = {0};
-
-static int acquire_cslot(int device)
-{
-    const char *off = getenv("ONEKA_B200_NO_CONST_WELLS");          // A/B switch: shared-memory well coordinates
-    if ((off && off[0] == '1') || device < 0 || device >= 64) return -1;
-    std::lock_guard<std::mutex> lk(g_slot_mu);
-    for (int i = 0; i < CONST_SLOTS; ++i)
-        if (!(g_slots_used[device] & (1u << i))) { g_slots_used[device] |= 1u << i; return i; }
-    return -1;
-}
-
-static void release_cslot(int device, int slot)
-{
-    if (slot < 0) return;
-    std::lock_guard<std::mutex> lk(g_slot_mu);
-    g_slots_used[device] &= ~(1u << slot);
-}
 
 // ------------------------------------------------------------------------------------------
 // Kernels
@@ -95,18 +71,32 @@ static void release_cslot(int device, int slot)
 __device__ __forceinline__ double cf_F(const TrackParams &tp, long long r) { return tp.coef[6 * r + 5]; }
 
 template <bool CONFINED>
-__device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc,
-                                                  double *s_wells)
+__device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc, double *s_wells)
 {
     const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
     const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
-    for (int i = threadIdx.x; i < ((tp.nw + 3) & ~3); i += blockDim.x) {            // layout: oneka_device.cuh, WELL_BLK
-        const bool real = i < tp.nw;
-        const double w = real ? tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale : 0.0;    // q/(2 pi) [/(H n)]
-        well_x(s_wells, i) = real ? tp.well_xy[2 * i] : 0.0;
-        well_y(s_wells, i) = real ? tp.well_xy[2 * i + 1] : 0.0;
-        well_w(s_wells, i) = w;
-        well_w32(s_wells, i) = (float)w;
+    if (CONFINED) {                                                                  // layout: oneka_device.cuh, SWELL_BLK
+        for (int j = threadIdx.x; j < ((tp.nw + 3) & ~3); j += blockDim.x) {
+            double b = 0.0, cx = 0.0, cy = 0.0;
+            if (j < tp.nw) {
+                const int i = j;
+                const double w = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;    // q/(2 pi H n)
+                b = (w != 0.0) ? 1.0 / w : 1e100;                                    // q = 0: the term becomes ~1e-100, i.e. nothing
+                cx = -(tp.well_xy[2 * i] - tp.xo) * b;
+                cy = -(tp.well_xy[2 * i + 1] - tp.yo) * b;
+            }
+            double *d = s_wells + (j >> 2) * SWELL_BLK + 3 * (j & 3);
+            d[0] = b; d[1] = cx; d[2] = cy;
+        }
+    } else {
+        for (int i = threadIdx.x; i < ((tp.nw + 3) & ~3); i += blockDim.x) {        // layout: oneka_device.cuh, WELL_BLK
+            const bool real = i < tp.nw;
+            const double w = real ? tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 : 0.0;    // q/(2 pi)
+            well_x(s_wells, i) = real ? tp.well_xy[2 * i] : 0.0;
+            well_y(s_wells, i) = real ? tp.well_xy[2 * i + 1] : 0.0;
+            well_w(s_wells, i) = w;
+            well_w32(s_wells, i) = (float)w;
+        }
     }
     if (threadIdx.x == 0) {
         const double *cf = tp.coef + 6 * r;
@@ -135,8 +125,9 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
 }
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
-template <bool CONFINED, int MODE, bool WPARAM>
-__device__ __forceinline__ void track_body(const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps, const WellXY *wxy)
+template <bool CONFINED, int MODE>
+__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
+track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
 {
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
@@ -149,22 +140,7 @@ __device__ __forceinline__ void track_body(const TrackParams &tp, const LatticeD
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
     stage_realization<CONFINED>(tp, r, rc, s_wells);
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE, WPARAM>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, wxy);
-}
-
-template <bool CONFINED, int MODE>
-__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
-track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
-{
-    track_body<CONFINED, MODE, false>(tp, L, bitmaps, nullptr);
-}
-
-// same, with the well coordinates read from constant-memory slot `cslot` (nw <= CONST_WELLS)
-template <bool CONFINED, int MODE>
-__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
-track_kernel_cw(TrackParams tp, LatticeDev L, unsigned int *bitmaps, int cslot)
-{
-    track_body<CONFINED, MODE, true>(tp, L, bitmaps, &c_wellxy[cslot]);
+    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P);
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per bitmap word position,
@@ -385,7 +361,7 @@ static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_d
 }
 
 // the well store of oneka_device.cuh (blocks of 4 wells, WELL_BLK doubles each) + 16 bytes of slack
-static size_t track_smem(int nw) { return (size_t)well_store_doubles(nw) * sizeof(double) + 16; }
+static size_t track_smem(int nw) { return (size_t)well_store_doubles(nw) * sizeof(double) + 256; }   // slack: the loops load the first well of the block after the last
 
 static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
 {
@@ -421,19 +397,6 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
     const size_t smem = track_smem(tp.nw);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
-    // (confined only: in the unconfined kernel ptxas does not keep the loop in uniform registers, the constant loads
-    //  become per-thread LDC.64 -- 8 per block against 4 LDS.128 -- and the shared-memory copy is the cheaper one)
-    if (ctx->cslot >= 0 && tp.nw > 0 && tp.nw <= CONST_WELLS && m->confined) {
-        // well coordinates -> this context's constant slot (device to device, stream-ordered: no host round trip)
-        CUDA_TRY(cudaMemcpyToSymbolAsync(c_wellxy, tp.well_xy, (size_t)tp.nw * 2 * sizeof(double),
-                                         (size_t)ctx->cslot * sizeof(WellXY), cudaMemcpyDeviceToDevice, ctx->stream));
-        prof_begin(ctx, 0);
-        track_kernel_cw<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ctx->cslot);
-        prof_end(ctx);
-        ctx->launches++;
-        CUDA_TRY(cudaGetLastError());
-        return ONEKA_OK;
-    }
     prof_begin(ctx, 0);
     if (m->confined) {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -527,7 +490,6 @@ oneka_ctx *oneka_create(int device)
     }
     if (reset_stats_async(ctx) != ONEKA_OK) { cudaFree(ctx->stats_dev); delete ctx; return nullptr; }
     cudaStreamSynchronize(ctx->stream);
-    ctx->cslot = acquire_cslot(device);
     g_err[0] = 0;
     return ctx;
 }
@@ -541,7 +503,6 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->bitmaps) cudaFree(ctx->bitmaps);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->stats_dev) cudaFree(ctx->stats_dev);
-    release_cslot(ctx->device, ctx->cslot);
     delete ctx;
 }
 

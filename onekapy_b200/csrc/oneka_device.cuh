@@ -38,7 +38,8 @@ struct RealConsts {
     double xo, yo;
 };
 
-// Wells in shared memory, blocks of 4 (WELL_BLK doubles = 112 bytes each, 16-byte aligned):
+// UNCONFINED wells in shared memory, blocks of 4 (WELL_BLK doubles = 112 bytes each, 16-byte aligned; the confined
+// store is SWELL_BLK, see field_feval):
 //   [0..7]  x0 y0 x1 y1 x2 y2 x3 y3      [8..11]  w0 w1 w2 w3 (scaled discharges)      [12..13]  the same w as 4 floats
 // One uniform base register addresses a whole block with immediate offsets (6 LDS.128 per 4 wells, 3 uniform
 // instructions of loop control); the last block may be partial (its unused slots are zero and never read by the
@@ -130,24 +131,40 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 //
 // confined   (stochastic.py:254-256 -> model.py:423-427 -> 300-315):
 //     -V = [ (2A dx + C dy + D) + sum_w q_w/(2 pi) (x-x_w)/r_w^2 ] / (H n)
-//   with every constant pre-divided by H*n when the CTA stages its realization, so one well
-//   costs 9 FP64-pipe instructions (2 DADD, 2 DMUL, 5 DFMA) + 1 MUFU.RCP64H + 1.5 LDS.128.
+//   SCALED WELLS: per well the store holds b = 1/w (w = q/(2 pi H n)) and c = -(well - origin) b.  With
+//   X = fma(x - xo, b, cx) = (x - x_w)/w and Y likewise, the well's term  w (x - x_w)/r^2  is  X / (X^2 + Y^2):
+//   the multiplication by w is gone -- 8 FP64-pipe instructions per well (4 DFMA for X, Y and the two sums, DMUL + DFMA
+//   for X^2 + Y^2, 2 DFMA of Newton) + 1 MUFU.RCP64H, for the reference's 15 flops.  Coordinates relative to the
+//   origin of the regional quadratic (= the target well, stochastic.py:239) keep the cancellation inside the FMA at
+//   2^-52 |x_w - xo| / |x - x_w|, <= ~1e-13 relative, the level of the Newton reciprocal; the target well's own
+//   c is exactly 0.  A well with q = 0 gets b = 1e100: its term is ~1e-100, i.e. nothing.
+//   (Tried and dropped, profiles/r01_notes.md: serving wells from constant memory through the uniform datapath.  With the
+//   unscaled 9-instruction form it removed the coordinate loads -- C4 +3.4 % -- but the scaled form needs TWO table
+//   operands in one FMA and an FP64 instruction takes only one uniform register: the second costs two MOVs per
+//   well, more than the LDS it replaces.  Scaled wells from shared memory are faster than either.)
 // unconfined (stochastic.py:258-260 -> model.py:377-389, 341-350, 226-237, 259-266):
-//   same discharge, plus Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi),
-//   head from Phi (two regimes), saturated thickness min(head, H); Phi <= 0 or head <= 0 is the
-//   reference's AquiferError -> PATH_AQUIFER_DRY.
-// Well coordinates are the same for every realization: up to CONST_WELLS of them are copied (device to device, on
-// the context's stream) into a slot of constant memory, from where the hot loop reads them through the UNIFORM
-// datapath (LDCU into uniform registers that the FP64 instructions take as operands) instead of one LDS.128 per
-// well on the vector issue port.  One slot per context (CONST_SLOTS per device and process; later contexts and
-// larger fields use the shared-memory copy).
-constexpr int CONST_WELLS = 256;
-constexpr int CONST_SLOTS = 12;
-struct __align__(16) WellXY { double xy[2 * CONST_WELLS + 8]; };
-__constant__ WellXY c_wellxy[CONST_SLOTS];
+//   same discharge (9 FP64 per well: the squared distance itself is needed), plus
+//   Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi), head from Phi (two regimes), saturated
+//   thickness min(head, H); Phi <= 0 or head <= 0 is the reference's AquiferError -> PATH_AQUIFER_DRY.
+// LDS.128 of the next block issued ahead (0, 2, 3 or 6; measured: 2 = 6 = +2 % over 0 on C3 and C4)
+#ifndef ONEKA_LDS_PREFETCH
+#define ONEKA_LDS_PREFETCH 2
+#endif
+constexpr int SWELL_BLK = 12;        // confined store: blocks of 4 wells x {b, cx, cy} = 6 LDS.128
+// confined, scaled: one well = 8 FP64-pipe instructions + MUFU.RCP64H
+__device__ __forceinline__ void scaled_term(double dx0, double dy0, double b, double cx, double cy, double &gx, double &gy)
+{
+    const double X = fma(dx0, b, cx);
+    const double Y = fma(dy0, b, cy);
+    const double rho = fma(Y, Y, X * X);
+    double y0, t;
+    rcp_parts(rho, y0, t);
+    const double yv = fma(y0, t, y0);
+    gx = fma(yv, X, gx);
+    gy = fma(yv, Y, gy);
+}
 
-// one well's term of the sum: 9 FP64-pipe instructions + MUFU.RCP64H
-template <bool CONFINED>
+// unconfined: one well = 9 FP64-pipe instructions + MUFU.RCP64H (+ F2F, MUFU.LG2, FFMA of the screening sum)
 __device__ __forceinline__ void well_term(double x, double y, double xw, double yw, double w, float w32,
                                           double &gx, double &gy, float &lsum32)
 {
@@ -160,63 +177,114 @@ __device__ __forceinline__ void well_term(double x, double y, double xw, double 
     const double s = fma(s0, t, s0);
     gx = fma(s, dx, gx);
     gy = fma(s, dy, gy);
-    if (!CONFINED) {
-        // bare MUFU.LG2 (no denormal scaling: (float) r2 is a normal number for 1e-19 m < r < 1e19 m; outside, the
-        // screening value is inf or nan and the comparison in field_feval sends a pumping well's neighbourhood to the FP64 path)
-        float l2;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((float)r2));
-        lsum32 = fmaf(w32, l2, lsum32);
-    }
+    // bare MUFU.LG2 (no denormal scaling: (float) r2 is a normal number for 1e-19 m < r < 1e19 m; outside, the
+    // screening value is inf or nan and the comparison in field_feval sends a pumping well's neighbourhood to the FP64 path)
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((float)r2));
+    lsum32 = fmaf(w32, l2, lsum32);
 }
 
-template <bool CONFINED, bool WPARAM = false>
+template <bool CONFINED>
 __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
-                                           double x, double y, double &fx, double &fy, const WellXY *wxy = nullptr)
+                                           double x, double y, double &fx, double &fy)
 {
     const double dx0 = x - rc.xo;
     const double dy0 = y - rc.yo;
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
+    if (CONFINED) {
+        const double *p = s_wells;
+        const double *const pend = s_wells + (nw >> 2) * SWELL_BLK;
+#if ONEKA_LDS_PREFETCH == 2
+        // the first two LDS.128 of the NEXT block (its first well) are issued while the current block is computed (the
+        // store has a block of slack): the first chain of an iteration no longer waits for shared memory
+        double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1];
+#pragma unroll 1
+        for (; p != pend; p += SWELL_BLK) {
+            const double2 v0 = n0, v1 = n1;
+            const double2 v2 = reinterpret_cast<const double2 *>(p)[2], v3 = reinterpret_cast<const double2 *>(p)[3];
+            const double2 v4 = reinterpret_cast<const double2 *>(p)[4], v5 = reinterpret_cast<const double2 *>(p)[5];
+            n0 = reinterpret_cast<const double2 *>(p)[6];
+            n1 = reinterpret_cast<const double2 *>(p)[7];
+            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
+            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
+            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
+            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
+        }
+#elif ONEKA_LDS_PREFETCH == 3
+        double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1], n2 = reinterpret_cast<const double2 *>(p)[2];
+#pragma unroll 1
+        for (; p != pend; p += SWELL_BLK) {
+            const double2 v0 = n0, v1 = n1, v2 = n2;
+            const double2 v3 = reinterpret_cast<const double2 *>(p)[3];
+            const double2 v4 = reinterpret_cast<const double2 *>(p)[4], v5 = reinterpret_cast<const double2 *>(p)[5];
+            n0 = reinterpret_cast<const double2 *>(p)[6];
+            n1 = reinterpret_cast<const double2 *>(p)[7];
+            n2 = reinterpret_cast<const double2 *>(p)[8];
+            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
+            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
+            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
+            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
+        }
+#elif ONEKA_LDS_PREFETCH == 6
+        double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1], n2 = reinterpret_cast<const double2 *>(p)[2];
+        double2 n3 = reinterpret_cast<const double2 *>(p)[3], n4 = reinterpret_cast<const double2 *>(p)[4], n5 = reinterpret_cast<const double2 *>(p)[5];
+#pragma unroll 1
+        for (; p != pend; p += SWELL_BLK) {
+            const double2 v0 = n0, v1 = n1, v2 = n2, v3 = n3, v4 = n4, v5 = n5;
+            n0 = reinterpret_cast<const double2 *>(p)[6];
+            n1 = reinterpret_cast<const double2 *>(p)[7];
+            n2 = reinterpret_cast<const double2 *>(p)[8];
+            n3 = reinterpret_cast<const double2 *>(p)[9];
+            n4 = reinterpret_cast<const double2 *>(p)[10];
+            n5 = reinterpret_cast<const double2 *>(p)[11];
+            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
+            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
+            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
+            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
+        }
+#else
+#pragma unroll 1
+        for (; p != pend; p += SWELL_BLK) {
+            const double2 v0 = reinterpret_cast<const double2 *>(p)[0], v1 = reinterpret_cast<const double2 *>(p)[1];
+            const double2 v2 = reinterpret_cast<const double2 *>(p)[2], v3 = reinterpret_cast<const double2 *>(p)[3];
+            const double2 v4 = reinterpret_cast<const double2 *>(p)[4], v5 = reinterpret_cast<const double2 *>(p)[5];
+            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
+            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
+            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
+            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
+        }
+#endif
+        const int rem = nw & 3;
+        if (rem > 0) scaled_term(dx0, dy0, p[0], p[1], p[2], gx, gy);
+        if (rem > 1) scaled_term(dx0, dy0, p[3], p[4], p[5], gx, gy);
+        if (rem > 2) scaled_term(dx0, dy0, p[6], p[7], p[8], gx, gy);
+        fx = gx;
+        fy = gy;
+        return PATH_OK;
+    }
     // unconfined: FP32 screening sum of  w_i log2(r_i^2)  (MUFU.LG2 on the XU pipe; the exact FP64 logs below are
     // needed only where the aquifer is not fully saturated)
     float lsum32 = 0.0f;
     const double *p = s_wells;
-    if (WPARAM) {
-        const int nb = nw >> 2;
-        // coordinates of the NEXT block are fetched (uniform loads) while the current one is computed; the slot is
-        // padded by one block, so the read past the last full block is in bounds
-        const double *c = wxy->xy;
-        double n0 = c[0], n1 = c[1], n2 = c[2], n3 = c[3], n4 = c[4], n5 = c[5], n6 = c[6], n7 = c[7];
-#pragma unroll 1
-        for (int b = 0; b < nb; ++b, p += WELL_BLK) {
-            const double x0 = n0, y0 = n1, x1 = n2, y1 = n3, x2 = n4, y2 = n5, x3 = n6, y3 = n7;
-            c += 8;
-            n0 = c[0]; n1 = c[1]; n2 = c[2]; n3 = c[3]; n4 = c[4]; n5 = c[5]; n6 = c[6]; n7 = c[7];
-            const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
-            const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
-            float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
-            well_term<CONFINED>(x, y, x0, y0, w01.x, wf.x, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, x1, y1, w01.y, wf.y, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, x2, y2, w23.x, wf.z, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, x3, y3, w23.y, wf.w, gx, gy, lsum32);
-        }
-    } else {
+    {
         const double *const pend = s_wells + (nw >> 2) * WELL_BLK;
+        // the first well of the NEXT block (coordinates and discharges) is loaded ahead, as in the confined loop
+        double2 nc0 = reinterpret_cast<const double2 *>(p)[0], nw01 = reinterpret_cast<const double2 *>(p)[4];
 #pragma unroll 1
         for (; p != pend; p += WELL_BLK) {
-            const double2 c0 = reinterpret_cast<const double2 *>(p)[0];
+            const double2 c0 = nc0, w01 = nw01;
+            nc0 = reinterpret_cast<const double2 *>(p)[7];
+            nw01 = reinterpret_cast<const double2 *>(p)[11];
             const double2 c1 = reinterpret_cast<const double2 *>(p)[1];
             const double2 c2 = reinterpret_cast<const double2 *>(p)[2];
             const double2 c3 = reinterpret_cast<const double2 *>(p)[3];
-            const double2 w01 = reinterpret_cast<const double2 *>(p)[4];
             const double2 w23 = reinterpret_cast<const double2 *>(p)[5];
-            float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!CONFINED) wf = reinterpret_cast<const float4 *>(p)[6];
-            well_term<CONFINED>(x, y, c0.x, c0.y, w01.x, wf.x, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, c1.x, c1.y, w01.y, wf.y, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, c2.x, c2.y, w23.x, wf.z, gx, gy, lsum32);
-            well_term<CONFINED>(x, y, c3.x, c3.y, w23.y, wf.w, gx, gy, lsum32);
+            const float4 wf = reinterpret_cast<const float4 *>(p)[6];
+            well_term(x, y, c0.x, c0.y, w01.x, wf.x, gx, gy, lsum32);
+            well_term(x, y, c1.x, c1.y, w01.y, wf.y, gx, gy, lsum32);
+            well_term(x, y, c2.x, c2.y, w23.x, wf.z, gx, gy, lsum32);
+            well_term(x, y, c3.x, c3.y, w23.y, wf.w, gx, gy, lsum32);
         }
     }
     {   // the last, partial block: single wells
@@ -224,22 +292,18 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
         const float *pf = reinterpret_cast<const float *>(p + 12);
         if (rem > 0) {
             const double2 c = reinterpret_cast<const double2 *>(p)[0];
-            well_term<CONFINED>(x, y, c.x, c.y, p[8], CONFINED ? 0.f : pf[0], gx, gy, lsum32);
+            well_term(x, y, c.x, c.y, p[8], pf[0], gx, gy, lsum32);
         }
         if (rem > 1) {
             const double2 c = reinterpret_cast<const double2 *>(p)[1];
-            well_term<CONFINED>(x, y, c.x, c.y, p[9], CONFINED ? 0.f : pf[1], gx, gy, lsum32);
+            well_term(x, y, c.x, c.y, p[9], pf[1], gx, gy, lsum32);
         }
         if (rem > 2) {
             const double2 c = reinterpret_cast<const double2 *>(p)[2];
-            well_term<CONFINED>(x, y, c.x, c.y, p[10], CONFINED ? 0.f : pf[2], gx, gy, lsum32);
+            well_term(x, y, c.x, c.y, p[10], pf[2], gx, gy, lsum32);
         }
     }
-    if (CONFINED) {
-        fx = gx;
-        fy = gy;
-        return PATH_OK;
-    } else {
+    {
         // regional part of the potential (model.py:226-231)
         const double pot_reg = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
         // Phi >= k H^2/2  <=>  head >= H  (model.py:345-349), and then V = Q/(H n) whatever Phi is (model.py:382-384;
@@ -556,10 +620,10 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // ------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
-template <bool CONFINED, int MODE, bool WPARAM = false>
+template <bool CONFINED, int MODE>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
-                                            long long r, int p, bool active, const WellXY *wxy = nullptr)
+                                            long long r, int p, bool active)
 {
     // Dormand-Prince tableau, capturezone.py:202-209
     constexpr double a20 = 1.0 / 5.0;
@@ -600,7 +664,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
             vout = tp.verts + ((size_t)r * tp.P + p) * (size_t)tp.max_verts * 2;
             if (tp.max_verts > 0) { vout[0] = x; vout[1] = y; }
         }
-        status = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, x, y, k1x, k1y, wxy);   // :219
+        status = field_feval<CONFINED>(rc, s_wells, nw, x, y, k1x, k1y);   // :219
         if (status != PATH_OK) running = false;
     }
 
@@ -622,26 +686,26 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y, wxy);      // :227
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
-                                           fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y, wxy);                                  // :228
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                                           fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                  // :228
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
-                                           fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y, wxy);                   // :229
+                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                                           fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                   // :229
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw,
+                st = field_feval<CONFINED>(rc, s_wells, nw,
                                            fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
-                                           fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y, wxy);    // :230
+                                           fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);    // :230
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw,
+                st = field_feval<CONFINED>(rc, s_wells, nw,
                                            fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
-                                           fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y, wxy);  // :231
+                                           fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);         // :233
                 const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
-                st = field_feval<CONFINED, WPARAM>(rc, s_wells, nw, xt, yt, k7x, k7y, wxy);                                            // :236
+                st = field_feval<CONFINED>(rc, s_wells, nw, xt, yt, k7x, k7y);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238

@@ -177,43 +177,9 @@ def test_c5_fine_grid_long_duration(eng):
     print("C5: lattice %dx%d (%.1f M nodes), steps %.3g, exact re-tests %d" % (geom.nrows, geom.ncols, geom.nrows * geom.ncols / 1e6, st["steps"], st["exact_tests"]))
 
 
-# ---- the two sources of well coordinates (constant-memory slot / shared memory) ---------------------------------
-def _engine_without_const_wells():
-    import os
-    from onekapy_b200.engine import Engine
-    os.environ["ONEKA_B200_NO_CONST_WELLS"] = "1"          # read by oneka_create
-    try:
-        return Engine(0)
-    finally:
-        del os.environ["ONEKA_B200_NO_CONST_WELLS"]
-
-
-@pytest.mark.parametrize("name,R,P,unconfined", [("c3", 24, 500, False), ("c4", 8, 300, False), ("c1", 16, 100, True)])
-def test_well_coordinate_sources_agree(eng, name, R, P, unconfined):
-    """Well coordinates read through the uniform datapath from the context's constant-memory slot (default) and
-    from the shared-memory well store (ONEKA_B200_NO_CONST_WELLS=1, > 256 wells, > 12 contexts): same arithmetic,
-    so grids, step counts and endpoints are identical bit for bit."""
-    import bench
-    spec, par, _ = bench.make_workload(name, R, P, 11, unconfined=unconfined)
-    other = _engine_without_const_wells()
-    out = []
-    for e in (eng, other):
-        dp = e.upload(spec, par)
-        geom, _ = lattice_for(eng, spec, eng.upload(spec, par))
-        counts = e.new_counts(geom)
-        e.reset_stats()
-        pp = e.capture(spec, dp, geom, counts, per_path=True)
-        st = e.read_stats()
-        out.append((counts.cpu().numpy(), pp["nverts"].cpu().numpy(), pp["end_xy"].cpu().numpy(), pp["status"].cpu().numpy(), st["attempts"]))
-    other.close()
-    a, b = out
-    assert a[4] == b[4] and a[4] > 0
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
-    assert np.array_equal(a[2], b[2], equal_nan=True)
-
-
-def test_more_wells_than_the_constant_slot(eng):
-    """300 wells (> CONST_WELLS = 256): the shared-memory coordinates, against the oracle."""
+# ---- large well fields / many contexts -------------------------------------------------------------------------
+def test_three_hundred_wells(eng):
+    """300 wells (a 33 KB well store per CTA), against the oracle."""
     from onekapy_b200 import synthetic
     from onekapy_b200.engine import FlowSpec
     pb = synthetic.well_field(300, seed=7)
@@ -228,8 +194,8 @@ def test_more_wells_than_the_constant_slot(eng):
     check_subset(eng, spec, par, np.array([0, 3]), geom)
 
 
-def test_more_contexts_than_constant_slots(eng):
-    """15 live contexts on one device: 12 get a constant-memory slot, the rest fall back; every one gives the same grid."""
+def test_many_contexts_on_one_device(eng):
+    """15 live contexts on one device give the same grid (each owns its stream-ordered workspace)."""
     from onekapy_b200.engine import Engine
     spec, par = workload("c3", 4, 96)
     geom, _ = lattice_for(eng, spec, eng.upload(spec, par))
