@@ -298,6 +298,22 @@ def run_ours(args):
     value = attempts / (ms * 1e-3)
     rps = reals / (ms * 1e-3)
 
+    # ---- rasteriser throughput (SURVEY.md 8d asks for it at C5): one more, untimed, step into a fresh grid ----
+    fresh = eng.new_counts(geom)
+    eng.reset_stats()
+    eng.capture(spec, dp, geom, fresh)
+    rst = eng.read_stats()
+    ragg = torch.tensor([float(fresh.sum(dtype=torch.int64).item()), float(rst["steps"]), float(rst["exact_tests"])], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(ragg, op=dist.ReduceOp.SUM)
+    cells_step, segs_step, exact_step = [float(v) for v in ragg.tolist()]
+    step_s = ms * 1e-3 / args.steps
+    raster = {"segments_per_s": segs_step / step_s, "cells_registered_per_s": cells_step / step_s,
+              "cells_registered_per_segment": cells_step / max(1.0, segs_step),
+              "exact_fp64_retests_per_segment": exact_step / max(1.0, segs_step),
+              "note": "cells registered = bits set in the per-realization bitmaps = sum of the count grid; every one is also one count increment of the flush"}
+    del fresh
+
     # ---- roofline of the fused tracking + raster kernel (this rank) ----
     probe_tf, _ = eng.fp64_probe(1 << 16)
     track_ms = kms["track_ms"] / max(1, kms["track_launches"])
@@ -362,7 +378,7 @@ def run_ours(args):
                 "realizations_per_s": rps, "accepted_steps_per_s": steps_acc / (ms * 1e-3),
                 "config": {"workload": label, "wells": nw, "lattice": [geom.nrows, geom.ncols], "l2": "flushed before every step (256 MiB write)",
                            "paths_not_ok": n_not_ok, "parallelism": "realizations sharded over %d GPU(s), one NCCL allreduce of the count grid per step" % world},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "raster": raster, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if group is not None:
