@@ -75,12 +75,30 @@ def make_workload(name, realizations, npaths, seed, unconfined=False):
         pb["confined"] = False
         label += ", confined=False"
     params = synthetic.sample_rows_fast(pb, R, seed)
+    make_workload.problem = pb
     xt, yt, rt = pb["wells"][pb["target"]][0:3]
     spec = FlowSpec(well_xy=np.array([[w[0], w[1]] for w in pb["wells"]], dtype=float), xtarget=float(xt),
                     ytarget=float(yt), rtarget=float(rt), npaths=P, duration=float(pb["duration"]), base=float(pb["base"]),
                     spacing=float(pb["spacing"]), umbra=float(pb["umbra"]), confined=bool(pb["confined"]),
                     tol=float(pb["tol"]), maxstep=float(pb["maxstep"]))
     return spec, params, label
+
+
+def host_sampling_rate(pb, R):
+    """Host share of the drop-in call (steps 1-4 of oneka/stochastic.py:186-199: variates, fit, A..F draw) for R
+    realizations of this problem, one core: the rate the GPU has to be fed at.  Not part of any timed region."""
+    from onekapy_b200.host.stochastic import sample_realizations
+    from onekapy_b200.host.utilities import filter_obs
+    obs = filter_obs(pb["observations"], pb["wells"], pb["buffer"])
+    xt, yt = pb["wells"][pb["target"]][0:2]
+    state = np.random.get_state()
+    t0 = time.perf_counter()
+    sample_realizations(R, pb["base"], pb["c_dist"], pb["p_dist"], pb["t_dist"], pb["wells"], obs, xt, yt,
+                        rng=np.random.default_rng(0), fit_method="qr", log_rows=False)
+    dt = time.perf_counter() - t0
+    np.random.set_state(state)
+    return {"realizations_per_s": R / dt, "cores": 1, "seconds": dt,
+            "what": "host.stochastic.sample_realizations(fit_method='qr'): reference-order variates, shared-QR fit, A..F draw"}
 
 
 def flops_per_attempt(nw):
@@ -372,14 +390,18 @@ def run_ours(args):
                "realizations_per_s": c["realizations"] / c["seconds"]}
 
     if rank == 0:
+        try:
+            host_rows = host_sampling_rate(make_workload.problem, R)
+        except Exception as exc:                             # informational only
+            host_rows = {"error": repr(exc)}
         line = {"metric": "particle-steps/s", "value": value, "unit": "DOPRI5 attempts/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "realizations_per_s": rps, "accepted_steps_per_s": steps_acc / (ms * 1e-3),
                 "config": {"workload": label, "wells": nw, "lattice": [geom.nrows, geom.ncols], "l2": "flushed before every step (256 MiB write)",
                            "paths_not_ok": n_not_ok, "parallelism": "realizations sharded over %d GPU(s), one NCCL allreduce of the count grid per step" % world},
-                "roofline": roofline, "raster": raster, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": sampler.summary()}
+                "roofline": roofline, "raster": raster, "cpu_baseline": cpu, "e2e": e2e, "host_sampling": host_rows,
+                "gpu_launches": int(launches), "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if group is not None:
         dist.barrier()

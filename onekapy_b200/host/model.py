@@ -174,28 +174,103 @@ def construct_fit_batch(obs, xo, yo, base, well_xy, q, cond, thick):
     return WA, Wb
 
 
-def fit_batch(obs, xo, yo, base, well_xy, q, cond, thick, method="lstsq"):
-    """Regional-flow fit for R realizations -> (coef_ev[R, 6], coef_cov[R, 6, 6]).
+def well_log_table(pts, well_xy):
+    """G[nw, n] = ln(r^2)/(4 pi) between wells and points: the realization-independent part of
+    compute_potential_wells_only (oneka/model.py:259-266); the wells' potential is q @ G."""
+    pts = np.asarray(pts, dtype=np.float64)
+    dx = pts[None, :, 0] - well_xy[:, None, 0]
+    dy = pts[None, :, 1] - well_xy[:, None, 1]
+    return np.log(dx * dx + dy * dy) * ONE_OVER_4PI
+
+
+def _fit_shared(obs, xo, yo, base, well_xy, q, cond, thick, regime):
+    """Fit for realizations whose observations are ALL in one regime of oneka/model.py:551-556.
+
+    There the weights factor: pot_std[r, o] = c_r s_o with (c_r, s_o) = (cond_r thick_r, z_std_o) when every
+    head >= thickness ("confined"), (cond_r, head_o z_std_o) when every head < thickness ("unconfined").  A common
+    scalar on the weights leaves the estimate alone, so ONE Householder QR of A / s serves every realization:
+        ev_r = pinv(A/s) ((pot_ev_r - wells_r)/s),   cov_r = c_r^2 inv((A/s)^T (A/s)),
+    and the wells' potential is the product q @ G.  The per-realization work is two small GEMMs."""
+    x, y, z_ev, z_std = obs[:, 0], obs[:, 1], obs[:, 2], obs[:, 3]
+    head = z_ev - base
+    cond = cond.reshape(-1, 1)
+    thick = thick.reshape(-1, 1)
+    if regime == "confined":
+        c = cond * thick
+        s = z_std
+        pot_ev = c * (head[None, :] - 0.5 * thick)
+    else:
+        c = cond
+        s = head * z_std
+        pot_ev = 0.5 * cond * (head ** 2 + z_std ** 2)[None, :]
+    dx = x - xo
+    dy = y - yo
+    A0 = np.stack([dx ** 2, dy ** 2, dx * dy, dx, dy, np.ones_like(dx)], axis=1) / s[:, None]
+    Q0, R0 = np.linalg.qr(A0)
+    R0inv = np.linalg.inv(R0)
+    pinv = R0inv @ Q0.T                                                  # [6, nobs]
+    C0 = R0inv @ R0inv.T
+    rhs = (pot_ev - q @ well_log_table(obs[:, :2], well_xy)) / s[None, :]
+    ev = rhs @ pinv.T
+    cov = (c * c)[:, :, None] * C0[None, :, :]
+    return ev, cov, c[:, 0], C0
+
+
+def mvn_factor(cov):
+    """F with  x = mean + z @ F  distributed N(mean, cov): numpy's Generator.multivariate_normal (method
+    'svd', what oneka/stochastic.py:241 calls) uses F = (u sqrt(s))^T with (u, s, _) = svd(cov).  Stacked."""
+    u, s, _ = np.linalg.svd(cov)
+    return np.swapaxes(u * np.sqrt(s)[..., None, :], -1, -2)
+
+
+def fit_batch(obs, xo, yo, base, well_xy, q, cond, thick, method="lstsq", with_factor=False):
+    """Regional-flow fit for R realizations -> (coef_ev[R, 6], coef_cov[R, 6, 6]) and, with_factor, the
+    multivariate-normal factors `mvn_factor(cov)` [R, 6, 6] (shared-QR rows: one svd, scaled by c_r).
 
     method="lstsq": per realization np.linalg.lstsq(rcond=-1) and inv(WA^T WA), i.e. the very
                     LAPACK calls of oneka/model.py:599,604 on identically built matrices;
-    method="qr":    one stacked Householder QR for all realizations (for R >~ 1e5):
-                    ev = R^-1 Q^T Wb, cov = R^-1 R^-T.  Same estimator, rounding differs."""
-    WA, Wb = construct_fit_batch(obs, xo, yo, base, well_xy, q, cond, thick)
-    R = WA.shape[0]
+    method="qr":    for R >~ 1e4.  Realizations whose observations all sit in one head regime (every
+                    shipped data set: heads of 80..420 m over 5..150 m of aquifer) share one QR
+                    (`_fit_shared`); the rest get one stacked Householder QR, ev = R^-1 Q^T Wb,
+                    cov = R^-1 R^-T.  Same estimator, rounding differs (~1e-9 relative on ev)."""
+    obs = np.asarray(obs, dtype=np.float64).reshape(-1, 4)
+    q = np.asarray(q, dtype=np.float64)
+    cond = np.asarray(cond, dtype=np.float64).reshape(-1)
+    thick = np.asarray(thick, dtype=np.float64).reshape(-1)
+    R = len(cond)
     ev = np.zeros((R, 6))
     cov = np.zeros((R, 6, 6))
+    fac = np.zeros((R, 6, 6)) if with_factor else None
     if method == "lstsq":
+        WA, Wb = construct_fit_batch(obs, xo, yo, base, well_xy, q, cond, thick)
         for i in range(R):
             e, c = Model.compute_fit(WA[i], Wb[i][:, None])
             ev[i] = e[:, 0]
             cov[i] = c
+        if with_factor:
+            fac[:] = mvn_factor(cov)
     elif method == "qr":
-        Q, Rm = np.linalg.qr(WA)                                          # stacked
-        rhs = np.einsum("rij,ri->rj", Q, Wb)
-        ev = np.linalg.solve(Rm, rhs[:, :, None])[:, :, 0]
-        Rinv = np.linalg.inv(Rm)
-        cov = Rinv @ np.transpose(Rinv, (0, 2, 1))
+        head = obs[:, 2] - base
+        if np.any(head <= 0):
+            raise RangeError("model.fit_coeficient: elevation < base")    # :558-559
+        all_conf = thick <= head.min()                                    # head >= thickness everywhere (:551)
+        all_unc = thick > head.max()
+        for rows, regime in ((all_conf, "confined"), (all_unc, "unconfined")):
+            if rows.any():
+                ev[rows], cov[rows], c, C0 = _fit_shared(obs, xo, yo, base, well_xy, q[rows], cond[rows], thick[rows],
+                                                       regime)
+                if with_factor:                                           # svd(c^2 C0) = (u, c^2 s, .)
+                    fac[rows] = c[:, None, None] * mvn_factor(C0)[None, :, :]
+        mixed = ~(all_conf | all_unc)
+        if mixed.any():
+            WA, Wb = construct_fit_batch(obs, xo, yo, base, well_xy, q[mixed], cond[mixed], thick[mixed])
+            Q, Rm = np.linalg.qr(WA)                                      # stacked
+            rhs = np.einsum("rij,ri->rj", Q, Wb)
+            ev[mixed] = np.linalg.solve(Rm, rhs[:, :, None])[:, :, 0]
+            Rinv = np.linalg.inv(Rm)
+            cov[mixed] = Rinv @ np.transpose(Rinv, (0, 2, 1))
+            if with_factor:
+                fac[mixed] = mvn_factor(cov[mixed])
     else:
         raise ValueError("method must be 'lstsq' or 'qr'")
-    return ev, cov
+    return (ev, cov, fac) if with_factor else (ev, cov)

@@ -25,33 +25,109 @@ class DistributionError(Error):
     """Invalid distribution specification (oneka/stochastic.py:65-72)."""
 
 
+def _legacy_rows(dists, nrows):
+    """[nrows, len(dists)] variates, consuming np.random's global stream exactly as the reference's
+    scalar calls do (oneka/stochastic.py:224-233 -> :297-304): realization by realization, one
+    `generate_random_variate` per entry of `dists` in order.
+
+    The legacy RandomState draws ONE double U per uniform / triangular variate and none for a Dirac
+    value, so the whole table comes from one `random_sample((nrows, nvariates))` block pushed through
+    NumPy's own formulas (legacy-distributions.c: uniform `lo + (hi - lo) U`; triangular by inversion,
+    `left + sqrt(U leftprod)` if `U <= ratio` else `right - sqrt((1 - U) rightprod)`).  Bit-identical
+    to the scalar loop (tests/test_host_logic.py::test_vectorised_sampling_is_the_scalar_stream)."""
+    out = np.empty((nrows, len(dists)))
+    rnd = []                                                  # columns that consume a double
+    for j, d in enumerate(dists):
+        if type(d) is not tuple:                              # Dirac (:297-298): the value itself
+            out[:, j] = d
+        elif len(d) == 2:
+            rnd.append(j)
+        elif len(d) == 3:
+            left, mode, right = d
+            if left > mode:                                   # the ValueErrors np.random.triangular raises
+                raise ValueError("left > mode")
+            if mode > right:
+                raise ValueError("mode > right")
+            if left == right:
+                raise ValueError("left == right")
+            rnd.append(j)
+        else:
+            raise DistributionError('<arg> must be a scalar, pair, or triple.')
+    if not rnd or nrows == 0:
+        return out
+    U = np.random.random_sample((nrows, len(rnd)))
+    for c, j in enumerate(rnd):
+        d = dists[j]
+        u = U[:, c]
+        if len(d) == 2:
+            out[:, j] = d[0] + (d[1] - d[0]) * u
+        else:
+            left, mode, right = (float(t) for t in d)
+            base = right - left
+            leftbase = mode - left
+            ratio = leftbase / base
+            leftprod = leftbase * base
+            rightprod = (right - mode) * base
+            lo = left + np.sqrt(u * leftprod)
+            hi = right - np.sqrt((1.0 - u) * rightprod)
+            out[:, j] = np.where(u <= ratio, lo, hi)
+    return out
+
+
+def _mvn_rows(rng, ev, factor):
+    """One `rng.multivariate_normal(ev[i], cov[i])` per row (oneka/stochastic.py:241), batched.
+
+    Generator.multivariate_normal (method='svd') is `mean + z @ (u sqrt(s)).T` with z = 6 standard
+    normals and (u, s, _) = svd(cov) -- `host.model.mvn_factor`; a [R, 6] block of normals is the same
+    stream as R calls, and the stacked LAPACK svd / matmul reproduce the per-row calls to summation-order
+    rounding, < 1e-12 standard deviations (tests/test_host_logic.py::test_vectorised_sampling_is_the_scalar_stream)."""
+    z = rng.standard_normal(ev.shape)
+    return ev + np.matmul(z[:, None, :], factor)[:, 0, :]
+
+
+SAMPLE_CHUNK = 32768          # realizations per host batch: bounds WA [chunk, nobs, 6] (160 MB at 100 observations)
+
+
 def sample_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, observations,
-                        xtarget, ytarget, rng=None, fit_method="lstsq", log_rows=True):
+                        xtarget, ytarget, rng=None, fit_method="auto", log_rows=True):
     """Steps (1)-(4) of oneka/stochastic.py:186-199 for all realizations -> RealizationParams.
 
-    RNG call order per realization is the reference's (:224-233): one variate per well, then
-    conductivity, porosity, thickness, all from np.random's global state.  A..F come from
-    `rng.multivariate_normal` -- the reference builds a fresh unseeded default_rng() per
-    realization (:241); pass a seeded Generator for reproducible rows."""
+    Vectorised over realizations, yet the rows are the ones the reference's loop would produce: the
+    discharges / conductivity / porosity / thickness consume np.random's global state in the
+    reference's order (`_legacy_rows`), and A..F come from `rng.multivariate_normal` row by row
+    (`_mvn_rows`) -- the reference builds a fresh unseeded default_rng() per realization (:241), so
+    without `rng` one unseeded Generator serves all rows; pass a seeded one for reproducible rows.
+
+    fit_method: "lstsq" = the reference's LAPACK calls per realization; "qr" = one stacked
+    factorisation (same estimator, rounding differs at ~1e-9 relative); "auto" = lstsq up to 4096
+    realizations, qr above."""
     nw = len(stochastic_wells)
-    q = np.zeros((nrealizations, nw))
-    k = np.zeros(nrealizations)
-    n = np.zeros(nrealizations)
-    H = np.zeros(nrealizations)
-    for i in range(nrealizations):
-        for j, w in enumerate(stochastic_wells):
-            q[i, j] = generate_random_variate(w[3])
-        k[i] = generate_random_variate(c_dist)
-        n[i] = generate_random_variate(p_dist)
-        H[i] = generate_random_variate(t_dist)
+    R = int(nrealizations)
+    dists = [w[3] for w in stochastic_wells] + [c_dist, p_dist, t_dist]
     wxy = np.array([[w[0], w[1]] for w in stochastic_wells], dtype=float).reshape(-1, 2)
     obs = np.array(observations, dtype=float).reshape(-1, 4)
-    ev, cov = fit_batch(obs, xtarget, ytarget, base, wxy, q, k, H, method=fit_method)
-    coef = np.zeros((nrealizations, 6))
-    for i in range(nrealizations):
-        g = rng if rng is not None else np.random.default_rng()
-        coef[i] = g.multivariate_normal(ev[i], cov[i])
-        if log_rows:
+    if fit_method == "auto":
+        fit_method = "lstsq" if R <= 4096 else "qr"
+    g = rng if rng is not None else np.random.default_rng()
+    q = np.zeros((R, nw))
+    k = np.zeros(R)
+    n = np.zeros(R)
+    H = np.zeros(R)
+    coef = np.zeros((R, 6))
+    ev = np.zeros((R, 6))
+    cov = np.zeros((R, 6, 6))
+    # all legacy variates first (their stream is independent of the Generator's), then fit + draw chunk by chunk
+    for r0 in range(0, R, SAMPLE_CHUNK):
+        r1 = min(R, r0 + SAMPLE_CHUNK)
+        rows = _legacy_rows(dists, r1 - r0)
+        q[r0:r1], k[r0:r1], n[r0:r1], H[r0:r1] = rows[:, :nw], rows[:, nw], rows[:, nw + 1], rows[:, nw + 2]
+    for r0 in range(0, R, SAMPLE_CHUNK):
+        r1 = min(R, r0 + SAMPLE_CHUNK)
+        ev[r0:r1], cov[r0:r1], fac = fit_batch(obs, xtarget, ytarget, base, wxy, q[r0:r1], k[r0:r1], H[r0:r1],
+                                               method=fit_method, with_factor=True)
+        coef[r0:r1] = _mvn_rows(g, ev[r0:r1], fac)
+    if log_rows and log.isEnabledFor(logging.INFO):
+        for i in range(R):
             recharge = 2 * (coef[i, 0] + coef[i, 1])
             log.info('Realization #{0:d}: {1:.2f}, {2:.2f}, {3:.2f}, {4:.2f}, {5:.4e}'
                      .format(i, base, k[i], n[i], H[i], recharge))

@@ -95,6 +95,89 @@ def test_sampling_reproduces_reference_rows(golden):
         assert np.allclose(par.coef, g["coef"], rtol=1e-7, atol=0)
 
 
+def test_vectorised_sampling_is_the_scalar_stream():
+    """sample_realizations draws whole tables at once; the rows must be the ones the reference's loop
+    (oneka/stochastic.py:220-241: per realization one variate per well, k, n, H from np.random, then one
+    multivariate_normal) produces from the same seeds: q, k, n, H and the fit bit for bit, A..F to 1e-12 standard deviations."""
+    pb = problems.load("basic")
+    wells = [(w[0], w[1], w[2], d) for w, d in zip(pb["wells"], [(500.0, 1000.0, 1800.0), (-300.0, 250.0)])]
+    wells.append((wells[0][0] + 900.0, wells[0][1] - 400.0, 0.3, 125.0))                # Dirac: consumes nothing
+    xt, yt = wells[0][0:2]
+    obs = filter_obs(pb["observations"], wells, pb["buffer"])
+    c_dist, p_dist, t_dist = (10.0, 50.0, 90.0), 0.2, (20.0, 25.0)
+    R = 37
+    np.random.seed(11)
+    par, ev, cov = sample_realizations(R, pb["base"], c_dist, p_dist, t_dist, wells, obs, xt, yt,
+                                       rng=np.random.default_rng(5), fit_method="lstsq", log_rows=False)
+    after = np.random.random_sample()                     # the global stream advanced by exactly the same amount
+    np.random.seed(11)
+    g = np.random.default_rng(5)
+    wxy = np.array([[w[0], w[1]] for w in wells])
+    for i in range(R):
+        q = [generate_random_variate(w[3]) for w in wells]
+        k, n, H = generate_random_variate(c_dist), generate_random_variate(p_dist), generate_random_variate(t_dist)
+        assert list(par.q[i]) == q and (par.cond[i], par.poro[i], par.thick[i]) == (k, n, H)
+        mo = Model(pb["base"], k, n, H, [(w[0], w[1], w[2], qq) for w, qq in zip(wells, q)])
+        e, c = mo.fit_regional_flow(obs, xt, yt)
+        assert np.array_equal(e[:, 0], ev[i]) and np.array_equal(c, cov[i])
+        sd = np.sqrt(np.diag(c))                          # same normals, same factor; BLAS summation order may differ
+        assert np.all(np.abs(g.multivariate_normal(e[:, 0], c) - par.coef[i]) <= 1e-12 * sd)
+    assert after == np.random.random_sample()
+    # chunking does not change the stream
+    import onekapy_b200.host.stochastic as hs
+    np.random.seed(11)
+    old, hs.SAMPLE_CHUNK = hs.SAMPLE_CHUNK, 8
+    try:
+        par2, _, _ = sample_realizations(R, pb["base"], c_dist, p_dist, t_dist, wells, obs, xt, yt,
+                                         rng=np.random.default_rng(5), fit_method="lstsq", log_rows=False)
+    finally:
+        hs.SAMPLE_CHUNK = old
+    assert np.array_equal(par2.q, par.q) and np.array_equal(par2.thick, par.thick) and np.array_equal(par2.coef, par.coef)
+    # the fast fit gives the same rows to rounding
+    np.random.seed(11)
+    par3, ev3, cov3 = sample_realizations(R, pb["base"], c_dist, p_dist, t_dist, wells, obs, xt, yt,
+                                          rng=np.random.default_rng(5), fit_method="qr", log_rows=False)
+    assert np.array_equal(par3.q, par.q) and np.allclose(ev3, ev, rtol=1e-7, atol=0)
+    sd = np.sqrt(np.einsum("rii->ri", cov))
+    assert np.all(np.abs(par3.coef - par.coef) <= 1e-6 * sd)
+    # the errors of the scalar calls
+    with pytest.raises(DistributionError):
+        sample_realizations(2, pb["base"], (1.0, 2.0, 3.0, 4.0), p_dist, t_dist, wells, obs, xt, yt)
+    with pytest.raises(ValueError):
+        sample_realizations(2, pb["base"], (3.0, 2.0, 4.0), p_dist, t_dist, wells, obs, xt, yt)
+    empty, _, _ = sample_realizations(0, pb["base"], c_dist, p_dist, t_dist, wells, obs, xt, yt)
+    assert len(empty) == 0
+
+
+@pytest.mark.parametrize("thick", [(20.0, 25.0), (130.0, 150.0), (60.0, 140.0)])
+def test_fit_qr_regimes_match_lstsq(thick):
+    """method="qr": shared-QR rows (all observations confined / all unconfined, oneka/model.py:551-556) and the
+    stacked factorisation of mixed rows against the reference's per-realization lstsq + inv."""
+    pb = problems.load("basic")                           # heads 80..120 m above the base
+    rng = np.random.default_rng(2)
+    R = 64
+    wxy = np.array([[w[0], w[1]] for w in pb["wells"]])
+    xt, yt = wxy[pb["target"]]
+    obs = np.array(filter_obs(pb["observations"], pb["wells"], pb["buffer"]), dtype=float)
+    q = rng.uniform(200.0, 2000.0, size=(R, len(wxy)))
+    k = rng.uniform(5.0, 80.0, size=R)
+    H = rng.uniform(thick[0], thick[1], size=R)
+    head = obs[:, 2] - pb["base"]
+    nconf = (head[None, :] >= H[:, None]).sum(axis=1)
+    if thick[1] < 80:
+        assert np.all(nconf == len(obs))
+    elif thick[0] > 120:
+        assert np.all(nconf == 0)
+    else:
+        assert np.any((nconf > 0) & (nconf < len(obs))) and np.any(nconf == len(obs))
+    ev, cov = fit_batch(obs, xt, yt, pb["base"], wxy, q, k, H, method="lstsq")
+    ev2, cov2, fac = fit_batch(obs, xt, yt, pb["base"], wxy, q, k, H, method="qr", with_factor=True)
+    sd = np.sqrt(np.einsum("rii->ri", cov))
+    assert np.all(np.abs(ev2 - ev) <= 1e-7 * sd + 1e-9 * np.abs(ev))
+    assert np.all(np.abs(cov2 - cov) <= 1e-6 * sd[:, :, None] * sd[:, None, :])
+    assert np.all(np.abs(np.swapaxes(fac, 1, 2) @ fac - cov2) <= 1e-9 * sd[:, :, None] * sd[:, None, :])   # F^T F = cov
+
+
 def test_variates():
     assert generate_random_variate(3.5) == 3.5
     assert compute_variate_mean(0.2) == 0.2
