@@ -257,6 +257,8 @@ def run_ours(args):
     if group is not None:
         dist.barrier()
     eng = Engine(local)
+    if args.farfield == "off":
+        eng.farfield = "off"
     dev = eng.device
     spec, params, label = make_workload(args.workload, args.realizations, args.npaths, args.seed + rank, args.unconfined)
     R, P, nw = len(params), spec.npaths, len(spec.well_xy)
@@ -302,6 +304,7 @@ def run_ours(args):
     barrier()
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
+    ff_info = eng.farfield_info()           # tiled far-field expansion of the well sum, or None = direct sums
     launches = eng.launch_count() - launches0
     stats = eng.read_stats()
     kms = eng.kernel_ms(reset=True)
@@ -399,7 +402,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "realizations_per_s": rps, "accepted_steps_per_s": steps_acc / (ms * 1e-3),
                 "config": {"workload": label, "wells": nw, "lattice": [geom.nrows, geom.ncols], "l2": "flushed before every step (256 MiB write)",
-                           "paths_not_ok": n_not_ok, "parallelism": "realizations sharded over %d GPU(s), one NCCL allreduce of the count grid per step" % world},
+                           "paths_not_ok": n_not_ok, "farfield": ff_info, "parallelism": "realizations sharded over %d GPU(s), one NCCL allreduce of the count grid per step" % world},
                 "roofline": roofline, "raster": raster, "cpu_baseline": cpu, "e2e": e2e, "host_sampling": host_rows,
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
@@ -421,6 +424,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20200725)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel A/B runs while tuning)")
+    ap.add_argument("--farfield", default="auto", choices=["auto", "off"],
+                    help="auto: tiled far-field expansion of the well sum where it pays (default); off: direct sums only")
     ap.add_argument("--unconfined", action="store_true", help="confined=False: the head-dependent velocity of model.py:353-389")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -171,6 +171,28 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
                           const double *coef_dev, const double *start_xy_dev, const int32_t *clip_dev,
                           uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev);
 
+/* ---- Far-field compression of the well sum (confined flow) ------------------------------------- *
+ * The reference adds one term per well at EVERY velocity evaluation (Model.compute_discharge,
+ * oneka/model.py:307-313: 15 flops x nw, six times per DOPRI5 attempt).  With this switched on, the capture
+ * entry points above evaluate the wells' part as  [direct sum over the few wells near the particle's tile]
+ * + [one complex polynomial of `order` terms for all the others]  on a grid of ntx x nty square tiles of side
+ * `tile` whose lower-left corner is (x0, y0): tiled local (Taylor) expansions of sum_w w/(z - z_w), wells farther
+ * than tile/(sqrt(2) eta) from a tile's centre being "far".  Truncation <= eta^order/(1 - eta) relative to a far
+ * term (3e-15 for eta = 0.3, order = 28); particles outside the grid, unconfined flow and models whose nw / xo / yo
+ * differ from the ones given here use the direct sum.  The tables depend on the well COORDINATES only (host pointer;
+ * must be the wells later passed as well_xy_dev); the realization-dependent coefficients are formed on the device
+ * per launch.  nw = 0 or order = 0 switches it off (the default).  Synchronous.
+ * max_near_out / mean_near_out (may be NULL): padded length of the longest near list, mean near wells per tile.   */
+int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
+                       double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
+                       int32_t *max_near_out, double *mean_near_out);
+/* Host restatement of the same tables and evaluation (NO GPU needed; test hook for the expansion's accuracy):
+ * out_host[npts][2] = sum_w w_host[w] (x - x_w)/r_w^2, sum_w w_host[w] (y - y_w)/r_w^2 evaluated the far-field way;
+ * near_count_out[npts] (may be NULL) = near wells summed directly, or -1 where the point lies outside the grid.   */
+int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const double *w_host, double xo, double yo,
+                             double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
+                             int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out);
+
 /* Statistics of everything enqueued since the last oneka_reset_stats.  Synchronises. */
 int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out);
 int oneka_reset_stats(oneka_ctx *ctx);

@@ -57,6 +57,17 @@ struct oneka_ctx {
     // host-buffer staging (oneka_capture_host), grow-only
     void *stage = nullptr;
     size_t stage_bytes = 0;
+    // far-field compression (oneka_set_farfield): tile geometry, static tables, per-launch coefficient workspace
+    struct FarField {
+        bool on = false;
+        int nw = 0, ntx = 0, nty = 0, order = 0, max_near = 0;
+        double xo = 0, yo = 0, gx0 = 0, gy0 = 0, tile = 0, eta = 0, mean_near = 0;
+        double2 *P = nullptr;                 // [ntiles][nw][order]
+        unsigned short *near_off = nullptr;   // [ntiles][max_near]
+        unsigned short *near_cnt = nullptr;   // [ntiles]
+        double2 *coef = nullptr;              // [realizations of a launch][ntiles][order], grow-only
+        size_t coef_bytes = 0;
+    } ff;
     // profiling
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kind; };
@@ -125,9 +136,11 @@ __device__ __forceinline__ void stage_realization(const TrackParams &tp, long lo
 }
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
-template <bool CONFINED, int MODE>
+// FF (confined only): the realization's far-field coefficient table and the tiles' near lists are staged behind the
+// well store (see "Far-field compression" in oneka_device.cuh).
+template <bool CONFINED, int MODE, bool FF>
 __global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
-track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
+track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff)
 {
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
@@ -138,9 +151,48 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps)
     const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long r = blockIdx.x / chunks;
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
-    stage_realization<CONFINED>(tp, r, rc, s_wells);
+    FarFieldShared fs = {nullptr, nullptr, nullptr};
+    if (FF) {
+        const int ntiles = ff.ntx * ff.nty;
+        double2 *s_coef = s_dyn + ff_store_double2(tp.nw);
+        unsigned short *s_off = reinterpret_cast<unsigned short *>(s_coef + ntiles * ff.order);
+        unsigned short *s_cnt = s_off + ntiles * ff.max_near;
+        const double2 *g = ff.coef + (size_t)r * ntiles * ff.order;
+        for (int i = threadIdx.x; i < ntiles * ff.order; i += blockDim.x) s_coef[i] = g[i];
+        for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_off[i] = ff.near_off[i];
+        for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = ff.near_cnt[i];
+        if (threadIdx.x == 0) {                                  // the dummy well that pads odd near lists: term ~1e-100
+            double *d = s_wells + ff_dummy_offset(tp.nw);
+            d[0] = 1e100; d[1] = 1.0; d[2] = 1.0;
+        }
+        fs.coef = s_coef; fs.off = s_off; fs.cnt = s_cnt;
+    }
+    stage_realization<CONFINED>(tp, r, rc, s_wells);             // ends with __syncthreads()
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P);
+    dopri_track<CONFINED, MODE, FF>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
+}
+
+// c[r][tile][k] = sum_w w_rw P[tile][w][k],  w_rw = q_rw / (2 pi H_r n_r)  (the scaling of stage_realization<true>).
+// One warp-sized CTA per (realization, tile), thread k = coefficient k; the P rows are read coalesced, q is a broadcast.
+__global__ void __launch_bounds__(32)
+farfield_coef_kernel(int nw, int ntiles, int order, const double2 *__restrict__ P, const double *__restrict__ q,
+                     const double *__restrict__ poro, const double *__restrict__ thick, double2 *__restrict__ out)
+{
+    const long long r = blockIdx.x / ntiles;
+    const int t = (int)(blockIdx.x % ntiles);
+    const double scale = 1.0 / (thick[r] * poro[r]);
+    const double *qr = q + (size_t)r * nw;
+    const double2 *Pt = P + (size_t)t * nw * order;
+    for (int k = threadIdx.x; k < order; k += 32) {
+        double ar = 0.0, ai = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            const double ww = qr[w] * 0.15915494309189535 * scale;
+            const double2 pk = Pt[(size_t)w * order + k];
+            ar = fma(ww, pk.x, ar);
+            ai = fma(ww, pk.y, ai);
+        }
+        out[((size_t)r * ntiles + t) * order + k] = make_double2(ar, ai);
+    }
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per bitmap word position,
@@ -388,27 +440,77 @@ static void prof_end(oneka_ctx *ctx)
     cudaEventRecord(ctx->events.back().b, ctx->stream);
 }
 
+static size_t ff_smem(const FarFieldDev &ff)
+{
+    const size_t nt = (size_t)ff.ntx * ff.nty;
+    return (nt * ff.order * sizeof(double2) + nt * ff.max_near * 2 + nt * 2 + 15) & ~(size_t)15;
+}
+
 template <int MODE>
-static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps)
+static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps,
+                        const FarFieldDev *ff = nullptr)
 {
     const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long nblk = tp.R * chunks;
     if (nblk <= 0) return ONEKA_OK;
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
-    const size_t smem = track_smem(tp.nw);
+    size_t smem = track_smem(tp.nw);
+    if (ff) smem += ff_smem(*ff);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
     prof_begin(ctx, 0);
-    if (m->confined) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<true, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps);
+    FarFieldDev none;
+    memset(&none, 0, sizeof(none));
+    if (m->confined && ff) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<true, MODE, true><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, *ff);
+    } else if (m->confined) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<true, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
     } else {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<false, MODE><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps);
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<false, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
     }
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return ONEKA_OK;
+}
+
+// Far-field coefficients for the realizations of one launch (rows already offset) -> ctx->ff.coef; fills `out`.
+// Returns ONEKA_OK with use = false when the far field is off or does not apply to this model.
+static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long nr, const double *q, const double *poro,
+                            const double *thick, FarFieldDev &out, bool &use)
+{
+    const oneka_ctx::FarField &f = ctx->ff;
+    use = f.on && m->confined && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
+    if (!use) return ONEKA_OK;
+    const int ntiles = f.ntx * f.nty;
+    const size_t need = (size_t)nr * ntiles * f.order * sizeof(double2);
+    if (need > ctx->ff.coef_bytes) {
+        if (ctx->ff.coef) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFree(ctx->ff.coef)); ctx->ff.coef = nullptr; ctx->ff.coef_bytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->ff.coef, need);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ONEKA_ERR_NOMEM, "cudaMalloc(%zu) for far-field coefficients failed: %s", need, cudaGetErrorString(e)); }
+        ctx->ff.coef_bytes = need;
+    }
+    const long long nblk = nr * ntiles;
+    if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many (realization, tile) pairs in one launch (%lld)", nblk);
+    farfield_coef_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, q, poro, thick, ctx->ff.coef);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    out.ntx = f.ntx; out.nty = f.nty; out.order = f.order; out.max_near = f.max_near;
+    out.gx0 = f.gx0; out.gy0 = f.gy0; out.inv_tile = 1.0 / f.tile;
+    out.coef = ctx->ff.coef; out.near_off = f.near_off; out.near_cnt = f.near_cnt;
+    return ONEKA_OK;
+}
+
+// realizations per launch so that the coefficient workspace stays below 2 GiB
+static long long farfield_batch(const oneka_ctx *ctx, long long want)
+{
+    const oneka_ctx::FarField &f = ctx->ff;
+    if (!f.on) return want;
+    const size_t per = (size_t)f.ntx * f.nty * f.order * sizeof(double2);
+    const long long cap = (long long)(((size_t)2 << 30) / per);
+    return want < cap ? want : (cap < 1 ? 1 : cap);
 }
 
 static int launch_flush(oneka_ctx *ctx, const LatticeDev &L, long long nslots, unsigned int *counts,
@@ -454,6 +556,73 @@ static double undkey(unsigned long long k)
     double v;
     memcpy(&v, &b, 8);
     return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Far-field tables (host): geometry only -- see "Far-field compression" in oneka_device.cuh
+// ------------------------------------------------------------------------------------------
+struct FFTables {
+    int ntiles = 0, max_near = 0;
+    double mean_near = 0.0;
+    std::vector<double2> P;                    // [ntiles][nw][order]; zero rows for near wells
+    std::vector<unsigned short> off, cnt;      // [ntiles][max_near] (padded with the dummy well), [ntiles] (even)
+    std::vector<int> near_flat, near_begin;    // unpadded near lists (host evaluator)
+};
+
+static int build_ff_tables(int nw, const double *well_xy, double xo, double yo, double gx0, double gy0, double tile,
+                           int ntx, int nty, int order, double eta, FFTables &T)
+{
+    if (nw < 1 || !well_xy) return fail(ONEKA_ERR_ARG, "far field needs nw >= 1 wells");
+    if (!(tile > 0.0) || ntx < 1 || nty < 1 || (long long)ntx * nty > 4096) return fail(ONEKA_ERR_ARG, "far field: bad tile grid %d x %d, tile %g", ntx, nty, tile);
+    if (order < 4 || order > 64 || (order & 1)) return fail(ONEKA_ERR_ARG, "far field: order must be even and in [4, 64]");
+    if (!(eta > 0.0 && eta < 0.9)) return fail(ONEKA_ERR_ARG, "far field: eta must be in (0, 0.9)");
+    if (ff_dummy_offset(nw) + 3 > 65535) return fail(ONEKA_ERR_ARG, "far field: too many wells for 16-bit store offsets");
+    const int ntiles = ntx * nty;
+    const long double h = (long double)tile / sqrtl(2.0L);
+    const long double rfar = h / (long double)eta;
+    T.ntiles = ntiles;
+    T.P.assign((size_t)ntiles * nw * order, make_double2(0.0, 0.0));
+    T.near_flat.clear();
+    T.near_begin.assign(ntiles + 1, 0);
+    int maxn = 0;
+    for (int tj = 0; tj < nty; ++tj)
+        for (int ti = 0; ti < ntx; ++ti) {
+            const int t = tj * ntx + ti;
+            const long double cx = (long double)gx0 + ((long double)ti + 0.5L) * tile;     // tile centre relative to (xo, yo)
+            const long double cy = (long double)gy0 + ((long double)tj + 0.5L) * tile;
+            for (int w = 0; w < nw; ++w) {
+                const long double dx = ((long double)well_xy[2 * w] - xo) - cx, dy = ((long double)well_xy[2 * w + 1] - yo) - cy;
+                const long double d2 = dx * dx + dy * dy;
+                if (!(sqrtl(d2) >= rfar)) { T.near_flat.push_back(w); continue; }          // near (or nan): summed directly
+                const long double ir = dx / d2, ii = -dy / d2;                              // 1/(z_w - z_c)
+                const long double ur = h * ir, ui = h * ii;                                 // h/(z_w - z_c)
+                long double tr = -ir, tim = -ii;                                            // term_0 = -1/(z_w - z_c)
+                double2 *row = &T.P[((size_t)t * nw + w) * order];
+                for (int k = 0; k < order; ++k) {
+                    row[k] = make_double2((double)tr, (double)tim);
+                    const long double nr = tr * ur - tim * ui, ni = tr * ui + tim * ur;
+                    tr = nr; tim = ni;
+                }
+            }
+            T.near_begin[t + 1] = (int)T.near_flat.size();
+            const int n = T.near_begin[t + 1] - T.near_begin[t];
+            if (n > maxn) maxn = n;
+        }
+    T.max_near = (maxn + 1) & ~1;
+    if (T.max_near < 2) T.max_near = 2;
+    T.mean_near = (double)T.near_flat.size() / ntiles;
+    const unsigned short dummy = (unsigned short)ff_dummy_offset(nw);
+    T.off.assign((size_t)ntiles * T.max_near, dummy);
+    T.cnt.assign(ntiles, 0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int n = T.near_begin[t + 1] - T.near_begin[t];
+        for (int i = 0; i < n; ++i) {
+            const int w = T.near_flat[T.near_begin[t] + i];
+            T.off[(size_t)t * T.max_near + i] = (unsigned short)((w >> 2) * SWELL_BLK + 3 * (w & 3));
+        }
+        T.cnt[t] = (unsigned short)((n + 1) & ~1);
+    }
+    return ONEKA_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -503,6 +672,10 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->bitmaps) cudaFree(ctx->bitmaps);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->stats_dev) cudaFree(ctx->stats_dev);
+    if (ctx->ff.P) cudaFree(ctx->ff.P);
+    if (ctx->ff.near_off) cudaFree(ctx->ff.near_off);
+    if (ctx->ff.near_cnt) cudaFree(ctx->ff.near_cnt);
+    if (ctx->ff.coef) cudaFree(ctx->ff.coef);
     delete ctx;
 }
 
@@ -555,6 +728,89 @@ int oneka_kernel_ms(oneka_ctx *ctx, double *track_ms, double *flush_ms, uint64_t
     if (flush_ms) *flush_ms = ctx->flush_ms;
     if (track_launches) *track_launches = ctx->track_launches;
     if (reset) { ctx->track_ms = ctx->flush_ms = 0.0; ctx->track_launches = 0; }
+    return ONEKA_OK;
+}
+
+int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
+                       double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
+                       int32_t *max_near_out, double *mean_near_out)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    oneka_ctx::FarField &f = ctx->ff;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));                      // launches in flight may still read the old tables
+    f.on = false;
+    if (f.P) { cudaFree(f.P); f.P = nullptr; }
+    if (f.near_off) { cudaFree(f.near_off); f.near_off = nullptr; }
+    if (f.near_cnt) { cudaFree(f.near_cnt); f.near_cnt = nullptr; }
+    if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
+    FFTables T;
+    int rc = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T);
+    if (rc) return rc;
+    FarFieldDev probe;
+    memset(&probe, 0, sizeof(probe));
+    probe.ntx = ntx; probe.nty = nty; probe.order = order; probe.max_near = T.max_near;
+    if (track_smem(nw) + ff_smem(probe) > 200 * 1024)
+        return fail(ONEKA_ERR_ARG, "far field: %d tiles x order %d do not fit in shared memory", T.ntiles, order);
+    CUDA_TRY(cudaMalloc(&f.P, T.P.size() * sizeof(double2)));
+    CUDA_TRY(cudaMalloc(&f.near_off, T.off.size() * sizeof(unsigned short)));
+    CUDA_TRY(cudaMalloc(&f.near_cnt, T.cnt.size() * sizeof(unsigned short)));
+    CUDA_TRY(cudaMemcpy(f.P, T.P.data(), T.P.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(f.near_off, T.off.data(), T.off.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(f.near_cnt, T.cnt.data(), T.cnt.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.max_near = T.max_near;
+    f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
+    f.on = true;
+    if (max_near_out) *max_near_out = T.max_near;
+    if (mean_near_out) *mean_near_out = T.mean_near;
+    return ONEKA_OK;
+}
+
+int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const double *w_host, double xo, double yo,
+                             double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
+                             int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out)
+{
+    if (npts < 0 || !w_host || (npts && (!pts_host || !out_host))) return fail(ONEKA_ERR_ARG, "bad argument to oneka_farfield_eval_host");
+    FFTables T;
+    int rc = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T);
+    if (rc) return rc;
+    // coefficients as farfield_coef_kernel forms them (w_host are the scaled discharges q/(2 pi H n))
+    std::vector<double2> coef((size_t)T.ntiles * order);
+    for (int t = 0; t < T.ntiles; ++t)
+        for (int k = 0; k < order; ++k) {
+            double ar = 0.0, ai = 0.0;
+            for (int w = 0; w < nw; ++w) {
+                const double2 pk = T.P[((size_t)t * nw + w) * order + k];
+                ar = fma(w_host[w], pk.x, ar);
+                ai = fma(w_host[w], pk.y, ai);
+            }
+            coef[(size_t)t * order + k] = make_double2(ar, ai);
+        }
+    const double gx0 = x0 - xo, gy0 = y0 - yo, inv_tile = 1.0 / tile;
+    for (int64_t i = 0; i < npts; ++i) {
+        const double dx0 = pts_host[2 * i] - xo, dy0 = pts_host[2 * i + 1] - yo;
+        int tile_i;
+        double zr, zi, gx = 0.0, gy = 0.0;
+        auto direct = [&](int w) {
+            const double dx = pts_host[2 * i] - well_xy_host[2 * w], dy = pts_host[2 * i + 1] - well_xy_host[2 * w + 1];
+            const double r2 = dx * dx + dy * dy;
+            gx += w_host[w] * dx / r2;
+            gy += w_host[w] * dy / r2;
+        };
+        if (!ff_locate(ntx, nty, gx0, gy0, inv_tile, dx0, dy0, tile_i, zr, zi)) {
+            for (int w = 0; w < nw; ++w) direct(w);
+            if (near_count_out) near_count_out[i] = -1;
+        } else {
+            for (int j = T.near_begin[tile_i]; j < T.near_begin[tile_i + 1]; ++j) direct(T.near_flat[j]);
+            double re, im;
+            ff_poly_eval(coef.data() + (size_t)tile_i * order, order, zr, zi, re, im);
+            gx += re;
+            gy -= im;
+            if (near_count_out) near_count_out[i] = T.near_begin[tile_i + 1] - T.near_begin[tile_i];
+        }
+        out_host[2 * i] = gx;
+        out_host[2 * i + 1] = gy;
+    }
     return ONEKA_OK;
 }
 
@@ -644,7 +900,12 @@ int oneka_trace(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy
     tp.nverts = nverts_dev; tp.status = status_dev; tp.attempts = attempts_dev;
     LatticeDev L;
     memset(&L, 0, sizeof(L));
-    return launch_track<2>(ctx, m, tp, L, nullptr);
+    if (farfield_batch(ctx, R) < R) return launch_track<2>(ctx, m, tp, L, nullptr);     // test hook: too many rows for one table
+    FarFieldDev ff;
+    bool use_ff = false;
+    rc = prepare_farfield(ctx, m, R, q_dev, poro_dev, thick_dev, ff, use_ff);
+    if (rc) return rc;
+    return launch_track<2>(ctx, m, tp, L, nullptr, use_ff ? &ff : nullptr);
 }
 
 int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntraces,
@@ -708,6 +969,7 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
     const int chunks = (P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long max_r = 0x7fffffffLL / chunks;
     if (slots > max_r) slots = max_r;
+    slots = farfield_batch(ctx, slots);
     for (long long r0 = 0; r0 < R; r0 += slots) {
         const long long nr = (r0 + slots < R) ? slots : R - r0;
         TrackParams tp = make_track(m, well_xy_dev, nr, P, q_dev + (size_t)r0 * m->nw, cond_dev + r0, poro_dev + r0,
@@ -718,13 +980,17 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
         tp.clip = clip_dev ? clip_dev + 4 * (size_t)r0 * P : nullptr;
         tp.path_bbox = path_bbox_dev ? path_bbox_dev + 4 * (size_t)r0 * P : nullptr;
         tp.slot_flags = (raster && flags_dev) ? flags_dev + r0 : nullptr;
+        FarFieldDev ff;
+        bool use_ff = false;
+        rc = prepare_farfield(ctx, m, nr, tp.q, tp.poro, tp.thick, ff, use_ff);
+        if (rc) return rc;
         if (raster) {
-            rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps);
+            rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps, use_ff ? &ff : nullptr);
             if (rc) return rc;
             rc = launch_flush(ctx, L, nr, counts_dev, tp.slot_flags);
             if (rc) return rc;
         } else {
-            rc = launch_track<0>(ctx, m, tp, L, nullptr);
+            rc = launch_track<0>(ctx, m, tp, L, nullptr, use_ff ? &ff : nullptr);
             if (rc) return rc;
         }
     }

@@ -337,6 +337,113 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
 }
 
 // ------------------------------------------------------------------------------------------
+// Far-field compression of the well sum (confined path): tiled local expansions.
+//
+// The reference adds one term per well at every velocity evaluation (model.py:307-313), 15 flops x Nw.  In complex
+// form the wells' part of the backtracking velocity is  G(z) = gx - i gy = sum_w w_w / (z - z_w),  z = (x - xo) + i (y - yo).
+// For a point z inside a square tile (centre z_c, half-diagonal h) and a well FAR from the tile, |z_w - z_c| >= h/eta,
+//     w/(z - z_w) = - sum_k  w (z - z_c)^k / (z_w - z_c)^(k+1),      |term k| <= |w|/|z_w - z_c| eta^k,
+// so ALL far wells of a tile collapse into ONE polynomial in zeta = (z - z_c)/h with coefficients
+//     c_k = sum_w w_w P[tile][w][k],    P[tile][w][k] = -(h/(z_w - z_c))^k / (z_w - z_c)   (geometry only, built once on the host),
+// and only the few NEAR wells of the tile are summed directly.  Truncated after `order` terms the relative error of a far
+// term is <= eta^order/(1 - eta) (3e-15 for eta = 0.3, order = 28), below the Newton reciprocal of the direct sum.
+// Per evaluation: ~4 order FP64 instructions of complex Horner + 8 per near well, instead of 8 Nw
+// (200-well field: ~6 near wells + 28 terms ~ 20 well-equivalents instead of 200).
+// The c_k depend on the realization (discharges, H, n): farfield_coef_kernel forms them per launch, each CTA copies its
+// realization's table (ntiles x order complex) into shared memory next to the well store.  A particle outside the
+// tile grid (or a field with too few wells to gain) takes the direct sum, so the result never depends on the grid
+// beyond rounding (~1e-15 relative to sum |terms|).
+struct FarFieldDev {
+    int ntx, nty, order, max_near;   // order even, >= 4; max_near even (lists are padded with the dummy well)
+    double gx0, gy0;                 // lower-left corner of the tile grid, relative to (xo, yo)
+    double inv_tile;                 // 1 / tile side
+    const double2 *coef;             // [R of this launch][ntx*nty][order]  (x = re, y = im)
+    const unsigned short *near_off;  // [ntx*nty][max_near]  offsets (in doubles) of the near wells in the confined well store
+    const unsigned short *near_cnt;  // [ntx*nty]            padded (even) list lengths
+};
+struct FarFieldShared { const double2 *coef; const unsigned short *off; const unsigned short *cnt; };
+// shared-memory layout of a tracking CTA: [well store + 256 B of slack][coef ntiles x order double2][near_off][near_cnt];
+// the dummy well {b = 1e100, c = (1, 1)} that pads odd near lists sits in the slack right behind the confined store
+__host__ __device__ __forceinline__ constexpr int ff_dummy_offset(int nw) { return ((nw + 3) >> 2) * 12; }                    // doubles
+__host__ __device__ __forceinline__ constexpr int ff_store_double2(int nw) { return (((nw + 3) >> 2) * 14 * 8 + 256) / 16; }  // double2s
+
+constexpr double FF_SQRT2 = 1.4142135623730951;
+
+// sum_{k < order} c_k zeta^k, two interleaved Horner chains in zeta^2 (even / odd powers): half the dependency depth
+template <typename C2>
+__host__ __device__ __forceinline__ void ff_poly_eval(const C2 *c, int order, double zr, double zi, double &re, double &im)
+{
+    const double wr = fma(zr, zr, -(zi * zi));
+    const double wi = 2.0 * (zr * zi);
+    double er = c[order - 2].x, ei = c[order - 2].y, orr = c[order - 1].x, oi = c[order - 1].y;
+#pragma unroll 2
+    for (int k = order - 4; k >= 0; k -= 2) {
+        const C2 ce = c[k], co = c[k + 1];
+        const double ner = fma(er, wr, fma(-ei, wi, ce.x));
+        const double nei = fma(er, wi, fma(ei, wr, ce.y));
+        const double nor = fma(orr, wr, fma(-oi, wi, co.x));
+        const double noi = fma(orr, wi, fma(oi, wr, co.y));
+        er = ner; ei = nei; orr = nor; oi = noi;
+    }
+    re = fma(orr, zr, fma(-oi, zi, er));
+    im = fma(orr, zi, fma(oi, zr, ei));
+}
+
+// tile of the point (dx0, dy0) [relative to (xo, yo)] and its scaled offset from the tile centre; false = outside the grid
+__host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0, double gy0, double inv_tile,
+                                                   double dx0, double dy0, int &tile, double &zr, double &zi)
+{
+    const double tx = (dx0 - gx0) * inv_tile, ty = (dy0 - gy0) * inv_tile;
+    if (!(tx >= 0.0 && tx < (double)ntx && ty >= 0.0 && ty < (double)nty)) return false;      // also nan
+    const int ti = (int)tx, tj = (int)ty;                                                      // trunc = floor for tx >= 0
+    tile = tj * ntx + ti;
+    zr = (tx - (double)ti - 0.5) * FF_SQRT2;                                                   // (x - x_c)/h,  h = tile/sqrt 2
+    zi = (ty - (double)tj - 0.5) * FF_SQRT2;
+    return true;
+}
+
+#ifdef __CUDACC__
+// the direct sum as an out-of-line call: the rare particle outside the tile grid
+__device__ __noinline__ void field_direct_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
+{
+    field_feval<true>(rc, s_wells, nw, x, y, fx, fy);
+}
+
+__device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
+                                              const FarFieldDev &ff, const FarFieldShared &fs,
+                                              double x, double y, double &fx, double &fy)
+{
+    const double dx0 = x - rc.xo;
+    const double dy0 = y - rc.yo;
+    int tile;
+    double zr, zi;
+    if (!ff_locate(ff.ntx, ff.nty, ff.gx0, ff.gy0, ff.inv_tile, dx0, dy0, tile, zr, zi)) {
+        field_direct_cold(rc, s_wells, nw, x, y, fx, fy);
+        return PATH_OK;
+    }
+    double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
+    double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
+    // near wells, two per trip (lists are padded to even length with the dummy well, whose term is ~1e-100)
+    const unsigned short *po = fs.off + tile * ff.max_near;
+    const int n = fs.cnt[tile];
+    double hx = 0.0, hy = 0.0;                                   // second accumulator pair: two independent chains
+#pragma unroll 1
+    for (int i = 0; i < n; i += 2) {
+        const unsigned int o2 = *reinterpret_cast<const unsigned int *>(po + i);
+        const double *p0 = s_wells + (o2 & 0xffffu), *p1 = s_wells + (o2 >> 16);
+        scaled_term(dx0, dy0, p0[0], p0[1], p0[2], gx, gy);
+        scaled_term(dx0, dy0, p1[0], p1[1], p1[2], hx, hy);
+    }
+    // far wells: one polynomial
+    double re, im;
+    ff_poly_eval(fs.coef + tile * ff.order, ff.order, zr, zi, re, im);
+    fx = (gx + hx) + re;
+    fy = (gy + hy) - im;
+    return PATH_OK;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Rasteriser.
 //
 // insert() (probabilityfield.py:296-310) marks every lattice node of the clipped window whose
@@ -620,11 +727,17 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // ------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
-template <bool CONFINED, int MODE>
+template <bool CONFINED, int MODE, bool FF = false>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
-                                            long long r, int p, bool active)
+                                            long long r, int p, bool active,
+                                            const FarFieldDev &ff = FarFieldDev(), const FarFieldShared &fs = FarFieldShared())
 {
+    // the velocity: direct sum over the wells, or (FF, confined only) near wells + the tile's far-field polynomial
+    auto feval = [&](double px, double py, double &ox, double &oy) -> int {
+        if constexpr (FF) return field_feval_ff(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
+        else return field_feval<CONFINED>(rc, s_wells, tp.nw, px, py, ox, oy);
+    };
     // Dormand-Prince tableau, capturezone.py:202-209
     constexpr double a20 = 1.0 / 5.0;
     constexpr double a30 = 3.0 / 40.0, a31 = 9.0 / 40.0;
@@ -664,7 +777,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
             vout = tp.verts + ((size_t)r * tp.P + p) * (size_t)tp.max_verts * 2;
             if (tp.max_verts > 0) { vout[0] = x; vout[1] = y; }
         }
-        status = field_feval<CONFINED>(rc, s_wells, nw, x, y, k1x, k1y);   // :219
+        status = feval(x, y, k1x, k1y);   // :219
         if (status != PATH_OK) running = false;
     }
 
@@ -686,26 +799,26 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
+                st = feval(fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a31, k2x, a30 * k1x), x),
+                st = feval(fma(dt, fma(a31, k2x, a30 * k1x), x),
                                            fma(dt, fma(a31, k2y, a30 * k1y), y), k3x, k3y);                                  // :228
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw, fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
+                st = feval(fma(dt, fma(a42, k3x, fma(a41, k2x, a40 * k1x)), x),
                                            fma(dt, fma(a42, k3y, fma(a41, k2y, a40 * k1y)), y), k4x, k4y);                   // :229
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw,
+                st = feval(
                                            fma(dt, fma(a53, k4x, fma(a52, k3x, fma(a51, k2x, a50 * k1x))), x),
                                            fma(dt, fma(a53, k4y, fma(a52, k3y, fma(a51, k2y, a50 * k1y))), y), k5x, k5y);    // :230
                 if (!CONFINED && st) { status = st; running = false; break; }
-                st = field_feval<CONFINED>(rc, s_wells, nw,
+                st = feval(
                                            fma(dt, fma(a64, k5x, fma(a63, k4x, fma(a62, k3x, fma(a61, k2x, a60 * k1x)))), x),
                                            fma(dt, fma(a64, k5y, fma(a63, k4y, fma(a62, k3y, fma(a61, k2y, a60 * k1y)))), y), k6x, k6y);  // :231
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double xt = fma(dt, fma(a75, k6x, fma(a74, k5x, fma(a73, k4x, fma(a72, k3x, a70 * k1x)))), x);         // :233
                 const double yt = fma(dt, fma(a75, k6y, fma(a74, k5y, fma(a73, k4y, fma(a72, k3y, a70 * k1y)))), y);
-                st = field_feval<CONFINED>(rc, s_wells, nw, xt, yt, k7x, k7y);                                            // :236
+                st = feval(xt, yt, k7x, k7y);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238

@@ -151,6 +151,14 @@ class Engine:
         self._L = _cabi.load()
         self._h = _cabi.create(self.index)
         self._geom_hint = {}
+        # far-field compression of the well sum (oneka_set_farfield): "auto" = wherever it pays, "off" = direct sums only
+        self.farfield = "off" if os.environ.get("ONEKA_FARFIELD", "auto").lower() in ("0", "off", "no") else "auto"
+        self.farfield_order = int(os.environ.get("ONEKA_FARFIELD_ORDER", "28"))
+        self.farfield_eta = float(os.environ.get("ONEKA_FARFIELD_ETA", "0.3"))
+        self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "64"))
+        self.farfield_min_wells = 12
+        self._ff_key = None
+        self._ff_info = None
         self.use_stream(torch.cuda.current_stream(self.device))
         if workspace_limit is not None:
             _cabi.check(self._L.oneka_set_workspace_limit(self._h, int(workspace_limit)))
@@ -200,6 +208,61 @@ class Engine:
         _cabi.check(self._L.oneka_fp64_probe(self._h, int(iters), C.byref(t), C.byref(ms)))
         return t.value, ms.value
 
+    # -- far-field compression of the well sum ------------------------------------------------------
+    def set_farfield(self, spec: Optional[FlowSpec], box=None, order=None, eta=None, max_tiles=None):
+        """Configure (or, with spec None, switch off) the tiled far-field expansion for `spec`'s wells on a tile grid
+        covering box = (xmin, xmax, ymin, ymax).  Returns dict(tile, ntx, nty, order, eta, mean_near, max_near)."""
+        if spec is None or box is None:
+            if self._ff_key is not None:
+                _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, None, None))
+            self._ff_key, self._ff_info = None, None
+            return None
+        order = int(order or self.farfield_order)
+        eta = float(eta or self.farfield_eta)
+        g = farfield_grid(box, int(max_tiles or self.farfield_max_tiles))
+        wxy = np.ascontiguousarray(spec.well_xy, dtype=np.float64).reshape(-1, 2)
+        mx, mean = C.c_int32(0), C.c_double(0.0)
+        _cabi.check(self._L.oneka_set_farfield(self._h, len(wxy), wxy.ctypes.data, float(spec.xtarget), float(spec.ytarget),
+                                               g["x0"], g["y0"], g["tile"], g["ntx"], g["nty"], order, eta,
+                                               C.byref(mx), C.byref(mean)))
+        info = dict(g, order=order, eta=eta, mean_near=mean.value, max_near=int(mx.value))
+        self._ff_key = (self._ff_wells_key(spec), tuple(float(v) for v in box))
+        self._ff_info = info
+        return info
+
+    def _ff_wells_key(self, spec):
+        return (len(spec.well_xy), float(spec.xtarget), float(spec.ytarget),
+                np.ascontiguousarray(spec.well_xy, dtype=np.float64).tobytes())
+
+    def _auto_farfield(self, spec: FlowSpec, geom: Optional[LatticeGeom]):
+        """Called before every capture: keep / build / drop the far-field tables for this spec and lattice.
+        Tracking-only calls (geom None) keep tables built for the same wells (a particle outside the tile grid takes
+        the direct sum anyway) and otherwise run direct."""
+        nw = len(spec.well_xy)
+        if self.farfield == "off" or not spec.confined or nw < self.farfield_min_wells:
+            if self._ff_key is not None:
+                self.set_farfield(None)
+            return
+        wkey = self._ff_wells_key(spec)
+        if geom is None:
+            if self._ff_key is not None and self._ff_key[0] != wkey:
+                self.set_farfield(None)
+            return
+        box = tuple(float(v) for v in (geom.xmin, geom.xmax, geom.ymin, geom.ymax))
+        key = (wkey, box)
+        if self._ff_key == key:
+            return
+        info = self.set_farfield(spec, box)
+        # cost model in well-equivalents (8 FP64 + loads per well): a near well ~1.3, a polynomial term ~0.55
+        cost = 1.3 * (info["mean_near"] + 1.0) + 0.55 * info["order"] + 2.0
+        if cost >= 0.85 * nw:                                       # not worth it: drop the tables, remember the decision
+            _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, None, None))
+            self._ff_key, self._ff_info = key, None
+
+    def farfield_info(self):
+        """The active far-field configuration (None = direct sums)."""
+        return self._ff_info
+
     # -- Model.compute_* at points (oneka/model.py:207-427) -----------------------------------
     def eval_points(self, well_xy, q, base, cond, poro, thick, xo, yo, coef, pts):
         """-> [npts, 8] = potential, Qx, Qy, Vx_confined, Vy_confined, head, Vx, Vy."""
@@ -233,6 +296,7 @@ class Engine:
         status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
         attempts = torch.zeros((R, P), dtype=torch.int32, device=self.device)
         m = spec.model_desc()
+        self._auto_farfield(spec, None)
         _cabi.check(self._L.oneka_trace(self._h, C.byref(m), _ptr(dp.well_xy), R, P, _ptr(dp.q), _ptr(dp.cond),
                                         _ptr(dp.poro), _ptr(dp.thick), _ptr(dp.coef), _ptr(dp.start_xy),
                                         int(max_verts), _ptr(verts), _ptr(nverts), _ptr(status), _ptr(attempts)))
@@ -292,6 +356,7 @@ class Engine:
             status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
         m = spec.model_desc()
         lat = geom.as_lattice(spec.umbra) if geom is not None else None
+        self._auto_farfield(spec, geom)
         nvtx = self.torch.cuda.nvtx if os.environ.get("ONEKA_NVTX") else None      # ranges for nsys / ncu --nvtx
         if nvtx:
             nvtx.range_push("oneka.capture R=%d P=%d %s" % (R, P, "track+raster" if lat is not None else "track"))
@@ -338,6 +403,7 @@ class Engine:
         R, P = dp.R, int(dp.start_xy.shape[0])
         bb = torch.empty((R, P, 4), dtype=torch.float64, device=self.device)
         m = spec.model_desc()
+        self._auto_farfield(spec, None)
         _cabi.check(self._L.oneka_path_bboxes(self._h, C.byref(m), _ptr(dp.well_xy), R, P, _ptr(dp.q), _ptr(dp.cond),
                                               _ptr(dp.poro), _ptr(dp.thick), _ptr(dp.coef), _ptr(dp.start_xy),
                                               _ptr(bb), None))
@@ -413,6 +479,7 @@ class Engine:
         R, P = len(params), len(start_xy)
         m = spec.model_desc()
         lat = geom.as_lattice(spec.umbra) if geom is not None else None
+        self._auto_farfield(spec, geom)
         counts = None
         if geom is not None:
             counts = counts_out if counts_out is not None else np.zeros((geom.nrows, geom.ncols), dtype=np.uint32)
@@ -519,6 +586,21 @@ class Engine:
         if reuse_lattice and not rerun:
             self._geom_hint[key] = work_geom             # it fitted every realization: a good estimate for the next call
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
+
+
+def farfield_grid(box, max_tiles=64, min_tile=100.0):
+    """Square tiles covering box = (xmin, xmax, ymin, ymax): the smallest tile side >= min_tile with at most
+    max_tiles tiles (smaller tiles = fewer near wells per tile; the count is bounded by shared memory)."""
+    xmin, xmax, ymin, ymax = (float(v) for v in box)
+    W, H = max(xmax - xmin, 1.0), max(ymax - ymin, 1.0)
+    s = max(float(min_tile), np.sqrt(W * H / max_tiles))
+    while int(np.ceil(W / s)) * int(np.ceil(H / s)) > max_tiles:
+        s *= 1.02
+    ntx, nty = int(np.ceil(W / s)), int(np.ceil(H / s))
+    # centre the grid on the box
+    x0 = xmin - 0.5 * (ntx * s - W)
+    y0 = ymin - 0.5 * (nty * s - H)
+    return dict(x0=float(x0), y0=float(y0), tile=float(s), ntx=ntx, nty=nty)
 
 
 def _to_host(t):

@@ -1,0 +1,113 @@
+"""Far-field compression of the well sum (include/oneka_b200.h: oneka_set_farfield): accuracy of the tiled local
+expansions, checked WITHOUT a GPU through the library's host restatement of the same tables and evaluation
+(oneka_farfield_eval_host) against the reference's formula -- one term per well, oneka/model.py:307-313 -- summed in
+extended precision."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from onekapy_b200 import _cabi, problems, synthetic
+from onekapy_b200.engine import farfield_grid
+
+
+def _field(name):
+    pb = synthetic.well_field(200) if name == "c4" else problems.load(name)
+    wxy = np.array([[w[0], w[1]] for w in pb["wells"]], dtype=np.float64)
+    q = np.array([w[3][1] if isinstance(w[3], tuple) else w[3] for w in pb["wells"]], dtype=np.float64)
+    xo, yo = wxy[pb["target"]]
+    return wxy, q / (2 * np.pi * 20.0 * 0.25), float(xo), float(yo)
+
+
+def _eval(wxy, w, xo, yo, grid, order, eta, pts):
+    L = _cabi.load()
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.zeros((len(pts), 2))
+    near = np.zeros(len(pts), dtype=np.int32)
+    _cabi.check(L.oneka_farfield_eval_host(len(wxy), wxy.ctypes.data, w.ctypes.data, xo, yo, grid["x0"], grid["y0"],
+                                           grid["tile"], grid["ntx"], grid["nty"], order, eta, len(pts),
+                                           pts.ctypes.data, out.ctypes.data, near.ctypes.data))
+    return out, near
+
+
+def _direct_ld(wxy, w, pts):
+    """sum_w w (x - x_w)/r^2, sum_w w (y - y_w)/r^2 in long double, and sum |terms| (the scale rounding errors live on)."""
+    ld = np.longdouble
+    dx = pts[:, None, 0].astype(ld) - wxy[None, :, 0].astype(ld)
+    dy = pts[:, None, 1].astype(ld) - wxy[None, :, 1].astype(ld)
+    r2 = dx * dx + dy * dy
+    gx = (w.astype(ld) * dx / r2).sum(axis=1)
+    gy = (w.astype(ld) * dy / r2).sum(axis=1)
+    mag = (np.abs(w) / np.sqrt(r2.astype(np.float64))).sum(axis=1)
+    return gx, gy, mag
+
+
+@pytest.mark.parametrize("name,box", [("c4", (-600.0, 3400.0, -900.0, 900.0)), ("perham", (-1400.0, 1400.0, -1400.0, 1400.0)),
+                                      ("long_prairie", (-800.0, 800.0, -800.0, 800.0))])
+def test_expansion_matches_direct_sum(name, box):
+    wxy, w, xo, yo = _field(name)
+    grid = farfield_grid((xo + box[0], xo + box[1], yo + box[2], yo + box[3]), 64)
+    rng = np.random.default_rng(1)
+    n = 4000
+    pts = np.stack([rng.uniform(grid["x0"], grid["x0"] + grid["ntx"] * grid["tile"], n),
+                    rng.uniform(grid["y0"], grid["y0"] + grid["nty"] * grid["tile"], n)], axis=1)
+    # tile corners and edges are where |zeta| is largest and where the tile index flips
+    ii, jj = np.meshgrid(np.arange(grid["ntx"] + 1), np.arange(grid["nty"] + 1))
+    corners = np.stack([grid["x0"] + ii.ravel() * grid["tile"], grid["y0"] + jj.ravel() * grid["tile"]], axis=1)
+    pts = np.concatenate([pts, corners + 1e-9, corners - 1e-9])
+    far_from_wells = np.min(np.hypot(pts[:, None, 0] - wxy[None, :, 0], pts[:, None, 1] - wxy[None, :, 1]), axis=1) > 0.5
+    pts = pts[far_from_wells]
+    out, near = _eval(wxy, w, xo, yo, grid, 28, 0.3, pts)
+    gx, gy, mag = _direct_ld(wxy, w, pts)
+    err = np.maximum(np.abs(out[:, 0] - gx), np.abs(out[:, 1] - gy)).astype(np.float64) / mag
+    inside = near >= 0
+    assert inside.sum() > 3500
+    assert err.max() < 2e-14, err.max()                    # truncation 3e-15 of a far term + double rounding
+    assert np.all(near[inside] < len(wxy))
+    if len(wxy) >= 29:
+        assert near[inside].mean() < 0.45 * len(wxy)       # the point of it: most wells are in the polynomial
+    # points outside the grid take the direct sum
+    outside = np.array([[grid["x0"] - 5.0, grid["y0"] + 1.0], [grid["x0"] + grid["ntx"] * grid["tile"] + 1.0, grid["y0"] + 1.0],
+                        [np.nan, 0.0]])
+    o2, n2 = _eval(wxy, w, xo, yo, grid, 28, 0.3, outside)
+    assert list(n2) == [-1, -1, -1]
+    g2x, g2y, m2 = _direct_ld(wxy, w, outside[:2])
+    assert np.all(np.abs(o2[:2, 0] - g2x).astype(float) <= 1e-14 * m2)
+
+
+def test_every_well_is_counted_once():
+    """Unit weights on one well at a time: near list and polynomial partition the wells (no well lost or doubled)."""
+    wxy, w, xo, yo = _field("perham")
+    grid = farfield_grid((xo - 1000.0, xo + 1000.0, yo - 1000.0, yo + 1000.0), 16)
+    rng = np.random.default_rng(3)
+    pts = np.stack([rng.uniform(xo - 990, xo + 990, 50), rng.uniform(yo - 990, yo + 990, 50)], axis=1)
+    for j in range(len(wxy)):
+        e = np.zeros(len(wxy))
+        e[j] = 1.0
+        out, _ = _eval(wxy, e, xo, yo, grid, 28, 0.3, pts)
+        dx, dy = pts[:, 0] - wxy[j, 0], pts[:, 1] - wxy[j, 1]
+        r2 = dx * dx + dy * dy
+        assert np.allclose(out[:, 0], dx / r2, rtol=1e-12, atol=0) and np.allclose(out[:, 1], dy / r2, rtol=1e-12, atol=0)
+
+
+def test_order_controls_truncation():
+    wxy, w, xo, yo = _field("c4")
+    grid = farfield_grid((xo - 600.0, xo + 3400.0, yo - 900.0, yo + 900.0), 64)
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.uniform(xo - 500, xo + 3300, 1500), rng.uniform(yo - 800, yo + 800, 1500)], axis=1)
+    gx, gy, mag = _direct_ld(wxy, w, pts)
+    errs = []
+    for order in (8, 16, 28):
+        out, _ = _eval(wxy, w, xo, yo, grid, order, 0.3, pts)
+        errs.append(float((np.abs(out[:, 0] - gx).astype(np.float64) / mag).max()))
+    assert errs[0] > 1e-8 and errs[1] < 1e-8 and errs[2] < 2e-14 and errs[0] > errs[1] > errs[2]
+
+
+def test_bad_arguments():
+    L = _cabi.load()
+    wxy, w, xo, yo = _field("basic")
+    pts, out = np.zeros((1, 2)), np.zeros((1, 2))
+    for order, eta, ntx in [(27, 0.3, 4), (2, 0.3, 4), (28, 0.95, 4), (28, 0.3, 0), (28, 0.3, 5000)]:
+        rc = L.oneka_farfield_eval_host(len(wxy), wxy.ctypes.data, w.ctypes.data, xo, yo, 0.0, 0.0, 100.0, ntx, 4, order, eta,
+                                        1, pts.ctypes.data, out.ctypes.data, None)
+        assert rc == -1 and b"far field" in L.oneka_last_error()

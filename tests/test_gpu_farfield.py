@@ -1,0 +1,136 @@
+"""GPU tests of the far-field compression (tiled local expansions of the well sum, oneka_set_farfield).
+
+The expansion changes the velocity by ~1e-15 relative to sum |terms| (tests/test_farfield_host.py), so everything the
+direct sum is held to must still hold: the step SEQUENCE of every path (attempts, vertices), vertices within 1e-6
+relative of the executed reference's (observed ~1e-12), and count grids bit-exact against the executed reference and
+the oracle.  Particles that leave the tile grid fall back to the direct sum."""
+import numpy as np
+import pytest
+
+from helpers import traces_of
+from test_gpu_parity import spec_of, fixed_geom
+from test_gpu_properties import workload, lattice_for, check_subset
+
+pytestmark = pytest.mark.gpu
+POS_RTOL = 1e-6
+
+
+@pytest.fixture()
+def eng():
+    from onekapy_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _box(g):
+    v = g["verts"]
+    return (v[:, 0].min() - 50.0, v[:, 0].max() + 50.0, v[:, 1].min() - 50.0, v[:, 1].max() + 50.0)
+
+
+@pytest.mark.parametrize("tiles", [64, 9])
+def test_traces_with_farfield_vs_reference_and_direct(eng, golden, tiles):
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    dp = eng.upload(spec, par)
+    eng.farfield = "off"
+    direct = eng.trace(spec, dp, max_verts=1024)
+    assert eng.farfield_info() is None
+    eng.farfield = "auto"
+    info = eng.set_farfield(spec, _box(g), max_tiles=tiles)
+    assert info["ntx"] * info["nty"] <= tiles and info["mean_near"] < len(spec.well_xy)
+    ff = eng.trace(spec, dp, max_verts=1024)
+    assert eng.farfield_info() is not None                       # tracking-only calls keep the tables of the same wells
+    assert np.array_equal(ff["nverts"], direct["nverts"]) and np.array_equal(ff["attempts"], direct["attempts"])
+    assert (ff["status"] == 0).all()
+    ref = traces_of(g)
+    worst_ref = worst_dir = 0.0
+    for r in range(len(par)):
+        for p in range(s["P"]):
+            t = ref[r * s["P"] + p]
+            assert ff["nverts"][r, p] == len(t)
+            v = ff["verts"][r, p, :len(t)]
+            scale = np.maximum(np.abs(t).max(axis=1), 1.0)
+            worst_ref = max(worst_ref, (np.abs(v - t).max(axis=1) / scale).max())
+            worst_dir = max(worst_dir, (np.abs(v - direct["verts"][r, p, :len(t)]).max(axis=1) / scale).max())
+    print("perham traces, %d tiles (mean near %.1f of %d wells): max rel vertex error vs reference %.3e, vs direct sum %.3e"
+          % (info["ntx"] * info["nty"], info["mean_near"], len(spec.well_xy), worst_ref, worst_dir))
+    assert worst_ref < POS_RTOL and worst_dir < 1e-9
+
+
+def test_fused_capture_with_farfield_bit_exact(eng, golden):
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    dp = eng.upload(spec, par)
+    counts = eng.new_counts(gm)
+    eng.reset_stats()
+    pp = eng.capture(spec, dp, gm, counts, per_path=True)         # auto: 29 wells on this lattice
+    st = eng.read_stats()
+    info = eng.farfield_info()
+    assert info is not None, "far field should be active for 29 wells"
+    tr = traces_of(g)
+    assert np.array_equal(pp["nverts"].cpu().numpy().ravel(), [len(t) for t in tr])
+    assert st["steps"] == sum(len(t) - 1 for t in tr) and st["n_not_ok"] == 0
+    assert np.array_equal(counts.cpu().numpy().view(np.uint32), g["fixed_counts"].astype(np.uint32))
+    # same grid with the direct sum
+    eng.farfield = "off"
+    c2 = eng.new_counts(gm)
+    eng.reset_stats()
+    eng.capture(spec, dp, gm, c2)
+    st2 = eng.read_stats()
+    assert eng.farfield_info() is None
+    assert st2["attempts"] == st["attempts"] and np.array_equal(c2.cpu().numpy(), counts.cpu().numpy())
+
+
+def test_particles_outside_the_tile_grid_take_the_direct_sum(eng, golden):
+    """Tile grid over the lower-left quarter of the traces only: three quarters of the evaluations fall back."""
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    dp = eng.upload(spec, par)
+    x0, x1, y0, y1 = _box(g)
+    eng.set_farfield(spec, (x0, 0.5 * (x0 + x1), y0, 0.5 * (y0 + y1)), max_tiles=16)
+    out = eng.trace(spec, dp, max_verts=1024)
+    assert np.array_equal(out["nverts"].ravel(), [len(t) for t in traces_of(g)])
+    # fused: the engine would rebuild the tables for the lattice; call the C ABI's state as it is by keeping the key
+    eng._ff_key = (eng._ff_wells_key(spec), tuple(float(v) for v in (gm.xmin, gm.xmax, gm.ymin, gm.ymax)))
+    counts = eng.new_counts(gm)
+    eng.capture(spec, dp, gm, counts)
+    assert np.array_equal(counts.cpu().numpy().view(np.uint32), g["fixed_counts"].astype(np.uint32))
+
+
+def test_c4_farfield_vs_direct_and_oracle(eng):
+    spec, par = workload("c4", 6, 96)
+    dp = eng.upload(spec, par)
+    eng.farfield = "off"
+    geom, st0 = lattice_for(eng, spec, dp)
+    c_dir = eng.new_counts(geom)
+    eng.reset_stats()
+    eng.capture(spec, dp, geom, c_dir)
+    s_dir = eng.read_stats()
+    eng.farfield = "auto"
+    c_ff = eng.new_counts(geom)
+    eng.reset_stats()
+    eng.capture(spec, dp, geom, c_ff)
+    s_ff = eng.read_stats()
+    info = eng.farfield_info()
+    assert info is not None and info["mean_near"] < 30
+    print("C4: %d x %d tiles of %.0f m, order %d, mean near wells %.1f of 200" % (info["ntx"], info["nty"], info["tile"], info["order"], info["mean_near"]))
+    assert s_ff["attempts"] == s_dir["attempts"] and s_ff["steps"] == s_dir["steps"] and s_ff["n_not_ok"] == 0
+    assert np.array_equal(c_ff.cpu().numpy(), c_dir.cpu().numpy())
+    check_subset(eng, spec, par, np.array([1, 4]), geom)          # oracle: equal vertex counts, endpoints, grid
+
+
+def test_farfield_off_for_small_fields_and_unconfined(eng, golden):
+    g = golden("sto_basic.npz")                                   # 2 wells
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    assert eng.farfield_info() is None
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    spec.confined = False
+    gm = fixed_geom(g, s)
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    assert eng.farfield_info() is None
