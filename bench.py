@@ -344,11 +344,21 @@ def run_ours(args):
     # DRAM traffic of the fused kernel from the ncu --set full capture in profiles/ (27.9 MB per 1000 realizations of
     # the perham field, dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch: the path is not HBM-bound
     traffic = 27.9e6 * (R / 1000.0) if args.workload == "c3" else None
-    roofline = {"bound": "fp64", "kernel": "track_kernel<confined, raster>", "achieved": achieved, "peak": probe_tf,
+    # with the far-field compression the kernel EXECUTES fewer flops than the reference's formulation needs: per evaluation
+    # 20 (regional) + 16 per near well + 8 per polynomial term + ~16 of tile lookup, FMA = 2 (estimate from the mean near count)
+    if ff_info:
+        exec_flops = 6 * (20 + 16 * (ff_info["mean_near"] + 1.0) + 8 * ff_info["order"] + 16) + 137
+    else:
+        exec_flops = flops_per_attempt(nw)
+    roofline = {"bound": "fp64", "kernel": "track_kernel<confined, raster%s>" % (", far field" if ff_info else ""),
+                "achieved": achieved, "peak": probe_tf,
                 "unit": "TFLOP/s", "frac": achieved / probe_tf, "traffic": traffic,
                 "traffic_note": "bytes per launch scaled from profiles/r01_track_kernel_raw.csv (ncu --set full at R=1000); HBM is idle (0.01 % of peak), the bound is the FP64 pipe",
                 "peak_source": "in-run DFMA probe (oneka_fp64_probe); MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x max clock = %.1f" % nominal,
                 "flops_per_attempt": flops_per_attempt(nw), "attempts_per_launch": att_per_launch, "kernel_ms_per_launch": track_ms,
+                "flops_executed_per_attempt_estimate": exec_flops, "frac_executed_estimate": achieved * exec_flops / flops_per_attempt(nw) / probe_tf,
+                "frac_note": "achieved/frac count the ALGORITHMIC flops of the reference's formulation (257 + 90 Nw per attempt, SURVEY 8d); "
+                             "with the far-field compression active the kernel executes fewer (frac_executed_estimate), so frac may exceed 1",
                 "flush_kernel_ms_per_step": kms["flush_ms"] / args.steps,
                 "kernel_share_of_step": kms["track_ms"] / ms if world == 1 else None}
 

@@ -181,17 +181,19 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
  * term (3e-15 for eta = 0.3, order = 28); particles outside the grid, unconfined flow and models whose nw / xo / yo
  * differ from the ones given here use the direct sum.  The tables depend on the well COORDINATES only (host pointer;
  * must be the wells later passed as well_xy_dev); the realization-dependent coefficients are formed on the device
- * per launch.  nw = 0 or order = 0 switches it off (the default).  Synchronous.
+ * per launch.  Of the `order` terms the first order_fp64 are evaluated in FP64 and the rest -- whose coefficients are
+ * below 2^-24 of the far field once eta^order_fp64 <= 2^-24 -- in FP32 (order_fp64 = 0 chooses that split).
+ * nw = 0 or order = 0 switches it off (the default).  Synchronous.
  * max_near_out / mean_near_out (may be NULL): padded length of the longest near list, mean near wells per tile.   */
 int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
                        double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
-                       int32_t *max_near_out, double *mean_near_out);
+                       int32_t order_fp64, int32_t *max_near_out, double *mean_near_out);
 /* Host restatement of the same tables and evaluation (NO GPU needed; test hook for the expansion's accuracy):
  * out_host[npts][2] = sum_w w_host[w] (x - x_w)/r_w^2, sum_w w_host[w] (y - y_w)/r_w^2 evaluated the far-field way;
  * near_count_out[npts] (may be NULL) = near wells summed directly, or -1 where the point lies outside the grid.   */
 int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const double *w_host, double xo, double yo,
                              double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
-                             int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out);
+                             int32_t order_fp64, int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out);
 
 /* Statistics of everything enqueued since the last oneka_reset_stats.  Synchronises. */
 int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out);

@@ -100,9 +100,10 @@ def load():
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Stats)]
     L.oneka_fp64_probe.argtypes = [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.oneka_set_farfield.argtypes = [_vp, C.c_int32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
-                                     C.c_int32, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double)]
     L.oneka_farfield_eval_host.argtypes = [C.c_int32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
-                                           C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int64, _vp, _vp, _vp]
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64, _vp, _vp, _vp]
     for name in SYMBOLS:
         getattr(L, name)                  # AttributeError here = header / library mismatch
     _lib = L

@@ -60,10 +60,10 @@ struct oneka_ctx {
     // far-field compression (oneka_set_farfield): tile geometry, static tables, per-launch coefficient workspace
     struct FarField {
         bool on = false;
-        int nw = 0, ntx = 0, nty = 0, order = 0, max_near = 0;
+        int nw = 0, ntx = 0, nty = 0, order = 0, n64 = 0, max_near = 0;
         double xo = 0, yo = 0, gx0 = 0, gy0 = 0, tile = 0, eta = 0, mean_near = 0;
         double2 *P = nullptr;                 // [ntiles][nw][order]
-        unsigned short *near_off = nullptr;   // [ntiles][max_near]
+        unsigned int *near_off = nullptr;     // [ntiles][max_near] byte offsets into the well store
         unsigned short *near_cnt = nullptr;   // [ntiles]
         double2 *coef = nullptr;              // [realizations of a launch][ntiles][order], grow-only
         size_t coef_bytes = 0;
@@ -151,21 +151,27 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
     const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
     const long long r = blockIdx.x / chunks;
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
-    FarFieldShared fs = {nullptr, nullptr, nullptr};
+    FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
     if (FF) {
-        const int ntiles = ff.ntx * ff.nty;
-        double2 *s_coef = s_dyn + ff_store_double2(tp.nw);
-        unsigned short *s_off = reinterpret_cast<unsigned short *>(s_coef + ntiles * ff.order);
-        unsigned short *s_cnt = s_off + ntiles * ff.max_near;
-        const double2 *g = ff.coef + (size_t)r * ntiles * ff.order;
-        for (int i = threadIdx.x; i < ntiles * ff.order; i += blockDim.x) s_coef[i] = g[i];
+        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
+        double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
+        float2 *s_c32 = reinterpret_cast<float2 *>(s_c64 + ntiles * ff.n64);
+        unsigned int *s_off = reinterpret_cast<unsigned int *>(s_c32 + ntiles * ff.n32);
+        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
+        const double2 *g = ff.coef + (size_t)r * ntiles * order;
+        for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) {          // coalesced read of the realization's table
+            const int t = i / order, k = i - t * order;
+            const double2 c = g[i];
+            if (k < ff.n64) s_c64[t * ff.n64 + k] = c;
+            else s_c32[t * ff.n32 + (k - ff.n64)] = make_float2((float)c.x, (float)c.y);
+        }
         for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_off[i] = ff.near_off[i];
         for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = ff.near_cnt[i];
         if (threadIdx.x == 0) {                                  // the dummy well that pads odd near lists: term ~1e-100
             double *d = s_wells + ff_dummy_offset(tp.nw);
             d[0] = 1e100; d[1] = 1.0; d[2] = 1.0;
         }
-        fs.coef = s_coef; fs.off = s_off; fs.cnt = s_cnt;
+        fs.c64 = s_c64; fs.c32 = s_c32; fs.off = s_off; fs.cnt = s_cnt;
     }
     stage_realization<CONFINED>(tp, r, rc, s_wells);             // ends with __syncthreads()
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
@@ -443,7 +449,7 @@ static void prof_end(oneka_ctx *ctx)
 static size_t ff_smem(const FarFieldDev &ff)
 {
     const size_t nt = (size_t)ff.ntx * ff.nty;
-    return (nt * ff.order * sizeof(double2) + nt * ff.max_near * 2 + nt * 2 + 15) & ~(size_t)15;
+    return (nt * ff.n64 * sizeof(double2) + nt * ff.n32 * sizeof(float2) + nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
 }
 
 template <int MODE>
@@ -497,7 +503,7 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     farfield_coef_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, q, poro, thick, ctx->ff.coef);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
-    out.ntx = f.ntx; out.nty = f.nty; out.order = f.order; out.max_near = f.max_near;
+    out.ntx = f.ntx; out.nty = f.nty; out.n64 = f.n64; out.n32 = f.order - f.n64; out.max_near = f.max_near;
     out.gx0 = f.gx0; out.gy0 = f.gy0; out.inv_tile = 1.0 / f.tile;
     out.coef = ctx->ff.coef; out.near_off = f.near_off; out.near_cnt = f.near_cnt;
     return ONEKA_OK;
@@ -565,9 +571,23 @@ struct FFTables {
     int ntiles = 0, max_near = 0;
     double mean_near = 0.0;
     std::vector<double2> P;                    // [ntiles][nw][order]; zero rows for near wells
-    std::vector<unsigned short> off, cnt;      // [ntiles][max_near] (padded with the dummy well), [ntiles] (even)
+    std::vector<unsigned int> off;             // [ntiles][max_near] byte offsets into the well store (padded with the dummy well)
+    std::vector<unsigned short> cnt;           // [ntiles] padded (even) lengths
     std::vector<int> near_flat, near_begin;    // unpadded near lists (host evaluator)
 };
+
+// terms kept in FP64: the smallest even k with eta^k <= 2^-24 (see ff_tail_eval), at most `order`
+static int ff_split(int order, double eta, int order_fp64)
+{
+#if !ONEKA_FF_TAIL
+    (void)eta; (void)order_fp64;
+    return order;                               // this build evaluates every term in FP64
+#endif
+    if (order_fp64 > 0) { int k = (order_fp64 + 1) & ~1; return k < 2 ? 2 : (k > order ? order : k); }
+    int k = 2;
+    while (k < order && pow(eta, (double)k) > 5.9604644775390625e-08) k += 2;
+    return k > order ? order : k;
+}
 
 static int build_ff_tables(int nw, const double *well_xy, double xo, double yo, double gx0, double gy0, double tile,
                            int ntx, int nty, int order, double eta, FFTables &T)
@@ -576,7 +596,6 @@ static int build_ff_tables(int nw, const double *well_xy, double xo, double yo, 
     if (!(tile > 0.0) || ntx < 1 || nty < 1 || (long long)ntx * nty > 4096) return fail(ONEKA_ERR_ARG, "far field: bad tile grid %d x %d, tile %g", ntx, nty, tile);
     if (order < 4 || order > 64 || (order & 1)) return fail(ONEKA_ERR_ARG, "far field: order must be even and in [4, 64]");
     if (!(eta > 0.0 && eta < 0.9)) return fail(ONEKA_ERR_ARG, "far field: eta must be in (0, 0.9)");
-    if (ff_dummy_offset(nw) + 3 > 65535) return fail(ONEKA_ERR_ARG, "far field: too many wells for 16-bit store offsets");
     const int ntiles = ntx * nty;
     const long double h = (long double)tile / sqrtl(2.0L);
     const long double rfar = h / (long double)eta;
@@ -611,14 +630,15 @@ static int build_ff_tables(int nw, const double *well_xy, double xo, double yo, 
     T.max_near = (maxn + 1) & ~1;
     if (T.max_near < 2) T.max_near = 2;
     T.mean_near = (double)T.near_flat.size() / ntiles;
-    const unsigned short dummy = (unsigned short)ff_dummy_offset(nw);
+    if (T.max_near > 65534) return fail(ONEKA_ERR_ARG, "far field: near list too long");
+    const unsigned int dummy = (unsigned int)ff_dummy_offset(nw) * 8u;
     T.off.assign((size_t)ntiles * T.max_near, dummy);
     T.cnt.assign(ntiles, 0);
     for (int t = 0; t < ntiles; ++t) {
         const int n = T.near_begin[t + 1] - T.near_begin[t];
         for (int i = 0; i < n; ++i) {
             const int w = T.near_flat[T.near_begin[t] + i];
-            T.off[(size_t)t * T.max_near + i] = (unsigned short)((w >> 2) * SWELL_BLK + 3 * (w & 3));
+            T.off[(size_t)t * T.max_near + i] = (unsigned int)((w >> 2) * SWELL_BLK + 3 * (w & 3)) * 8u;
         }
         T.cnt[t] = (unsigned short)((n + 1) & ~1);
     }
@@ -733,7 +753,7 @@ int oneka_kernel_ms(oneka_ctx *ctx, double *track_ms, double *flush_ms, uint64_t
 
 int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
                        double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
-                       int32_t *max_near_out, double *mean_near_out)
+                       int32_t order_fp64, int32_t *max_near_out, double *mean_near_out)
 {
     if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -749,16 +769,17 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (rc) return rc;
     FarFieldDev probe;
     memset(&probe, 0, sizeof(probe));
-    probe.ntx = ntx; probe.nty = nty; probe.order = order; probe.max_near = T.max_near;
+    const int n64 = ff_split(order, eta, order_fp64);
+    probe.ntx = ntx; probe.nty = nty; probe.n64 = n64; probe.n32 = order - n64; probe.max_near = T.max_near;
     if (track_smem(nw) + ff_smem(probe) > 200 * 1024)
         return fail(ONEKA_ERR_ARG, "far field: %d tiles x order %d do not fit in shared memory", T.ntiles, order);
     CUDA_TRY(cudaMalloc(&f.P, T.P.size() * sizeof(double2)));
-    CUDA_TRY(cudaMalloc(&f.near_off, T.off.size() * sizeof(unsigned short)));
+    CUDA_TRY(cudaMalloc(&f.near_off, T.off.size() * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&f.near_cnt, T.cnt.size() * sizeof(unsigned short)));
     CUDA_TRY(cudaMemcpy(f.P, T.P.data(), T.P.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(f.near_off, T.off.data(), T.off.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(f.near_off, T.off.data(), T.off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_cnt, T.cnt.data(), T.cnt.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.max_near = T.max_near;
+    f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.n64 = n64; f.max_near = T.max_near;
     f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
     f.on = true;
     if (max_near_out) *max_near_out = T.max_near;
@@ -768,7 +789,7 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
 
 int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const double *w_host, double xo, double yo,
                              double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
-                             int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out)
+                             int32_t order_fp64, int64_t npts, const double *pts_host, double *out_host, int32_t *near_count_out)
 {
     if (npts < 0 || !w_host || (npts && (!pts_host || !out_host))) return fail(ONEKA_ERR_ARG, "bad argument to oneka_farfield_eval_host");
     FFTables T;
@@ -785,6 +806,16 @@ int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const doubl
                 ai = fma(w_host[w], pk.y, ai);
             }
             coef[(size_t)t * order + k] = make_double2(ar, ai);
+        }
+    // the split the device uses: low orders double2, the tail rounded to float2 (track_kernel's staging)
+    const int n64 = ff_split(order, eta, order_fp64), n32 = order - n64;
+    std::vector<float2> c32((size_t)T.ntiles * (n32 > 0 ? n32 : 1));
+    std::vector<double2> c64((size_t)T.ntiles * n64);
+    for (int t = 0; t < T.ntiles; ++t)
+        for (int k = 0; k < order; ++k) {
+            const double2 c = coef[(size_t)t * order + k];
+            if (k < n64) c64[(size_t)t * n64 + k] = c;
+            else c32[(size_t)t * n32 + (k - n64)] = make_float2((float)c.x, (float)c.y);
         }
     const double gx0 = x0 - xo, gy0 = y0 - yo, inv_tile = 1.0 / tile;
     for (int64_t i = 0; i < npts; ++i) {
@@ -803,7 +834,10 @@ int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const doubl
         } else {
             for (int j = T.near_begin[tile_i]; j < T.near_begin[tile_i + 1]; ++j) direct(T.near_flat[j]);
             double re, im;
-            ff_poly_eval(coef.data() + (size_t)tile_i * order, order, zr, zi, re, im);
+            float tr = 0.0f, ti = 0.0f;
+            if (n32 > 0) ff_tail_eval(c32.data() + (size_t)tile_i * n32, n32, (float)zr, (float)zi, tr, ti);
+            if (n32 > 0) ff_poly_eval<true>(c64.data() + (size_t)tile_i * n64, n64, zr, zi, (double)tr, (double)ti, re, im);
+            else ff_poly_eval<false>(c64.data() + (size_t)tile_i * n64, n64, zr, zi, 0.0, 0.0, re, im);
             gx += re;
             gy -= im;
             if (near_count_out) near_count_out[i] = T.near_begin[tile_i + 1] - T.near_begin[tile_i];

@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 namespace oneka {
 
@@ -354,30 +355,93 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
 // tile grid (or a field with too few wells to gain) takes the direct sum, so the result never depends on the grid
 // beyond rounding (~1e-15 relative to sum |terms|).
 struct FarFieldDev {
-    int ntx, nty, order, max_near;   // order even, >= 4; max_near even (lists are padded with the dummy well)
+    int ntx, nty;
+    int n64, n32;                    // terms evaluated in FP64 (even, >= 2) and in FP32 (the tail, >= 0): order = n64 + n32
+    int max_near;                    // even (lists are padded with the dummy well)
     double gx0, gy0;                 // lower-left corner of the tile grid, relative to (xo, yo)
     double inv_tile;                 // 1 / tile side
     const double2 *coef;             // [R of this launch][ntx*nty][order]  (x = re, y = im)
-    const unsigned short *near_off;  // [ntx*nty][max_near]  offsets (in doubles) of the near wells in the confined well store
+    const unsigned int *near_off;    // [ntx*nty][max_near]  BYTE offsets of the near wells in the confined well store
     const unsigned short *near_cnt;  // [ntx*nty]            padded (even) list lengths
 };
-struct FarFieldShared { const double2 *coef; const unsigned short *off; const unsigned short *cnt; };
-// shared-memory layout of a tracking CTA: [well store + 256 B of slack][coef ntiles x order double2][near_off][near_cnt];
+struct FarFieldShared { const double2 *c64; const float2 *c32; const unsigned int *off; const unsigned short *cnt; };
+// shared-memory layout of a tracking CTA:
+//   [well store + 256 B of slack][c64 ntiles x n64 double2][c32 ntiles x n32 float2][near_off][near_cnt];
 // the dummy well {b = 1e100, c = (1, 1)} that pads odd near lists sits in the slack right behind the confined store
 __host__ __device__ __forceinline__ constexpr int ff_dummy_offset(int nw) { return ((nw + 3) >> 2) * 12; }                    // doubles
 __host__ __device__ __forceinline__ constexpr int ff_store_double2(int nw) { return (((nw + 3) >> 2) * 14 * 8 + 256) / 16; }  // double2s
 
 constexpr double FF_SQRT2 = 1.4142135623730951;
 
-// sum_{k < order} c_k zeta^k, two interleaved Horner chains in zeta^2 (even / odd powers): half the dependency depth
-template <typename C2>
-__host__ __device__ __forceinline__ void ff_poly_eval(const C2 *c, int order, double zr, double zi, double &re, double &im)
+// Build knobs, all measured on B200 (profiles/r01_farfield_ab.txt; C3 perham / C4 200 wells, ms per step):
+//   defaults (all-FP64 polynomial, F2I / I2F tile lookup, no prefetch)        79.7 / 33.0
+//   ONEKA_FF_TAIL 1        high-order terms in FP32 (below)                    87.1 / 36.0   more code, more spills
+//   ONEKA_FF_LOCATE_CVT 0  tile index by the 1.5 * 2^52 trick                  84.8 / 34.9   + 9 instructions per evaluation
+//   ONEKA_FF_PREFETCH 1    next trip's coefficients loaded ahead               86.9 / 35.5   164 B of spills instead of 68
+//   evaluation as a __noinline__ call (half the code)                        105.6 / 42.9
+// The kernel sits at 80 registers with the Runge-Kutta stages live; whatever adds live values to the evaluation loses.
+#ifndef ONEKA_FF_TAIL
+#define ONEKA_FF_TAIL 0
+#endif
+#ifndef ONEKA_FF_LOCATE_CVT
+#define ONEKA_FF_LOCATE_CVT 1
+#endif
+#ifndef ONEKA_FF_PREFETCH
+#define ONEKA_FF_PREFETCH 0
+#endif
+// THE FP32 TAIL (ONEKA_FF_TAIL).  |c_k| <= S eta^k (S = sum over the far wells of |w|/|z_w - z_c|), so the terms k >= n64 with
+// eta^n64 <= 2^-24 contribute at most 2^-24 S: evaluated in FP32 (FFMA: half the issue cost of DFMA, on the otherwise idle
+// FP32 pipe) their rounding error is ~2^-23 x 2^-24 S = 7e-15 S, the level of the truncation itself.
+//   T = sum_{j < n} t_j zeta^j   (t_j = c_{n64 + j} as float2),  Horner, one chain
+template <typename F2>
+__host__ __device__ __forceinline__ void ff_tail_eval(const F2 *t, int n, float fr, float fi, float &tr, float &ti)
+{
+    float ar = 0.0f, ai = 0.0f;
+#pragma unroll 2
+    for (int j = n - 1; j >= 0; --j) {
+        const F2 c = t[j];
+        const float nr = fmaf(ar, fr, fmaf(-ai, fi, c.x));
+        const float ni = fmaf(ar, fi, fmaf(ai, fr, c.y));
+        ar = nr; ai = ni;
+    }
+    tr = ar; ti = ai;
+}
+
+// sum_{k < n64} c_k zeta^k + zeta^n64 (sr + i si): two interleaved Horner chains in w = zeta^2 (even / odd powers, half the
+// dependency depth); the tail value seeds the even chain as the coefficient of w^(n64/2)
+template <bool SEED, typename C2>
+__host__ __device__ __forceinline__ void ff_poly_eval(const C2 *c, int n64, double zr, double zi, double sr, double si,
+                                                      double &re, double &im)
 {
     const double wr = fma(zr, zr, -(zi * zi));
     const double wi = 2.0 * (zr * zi);
-    double er = c[order - 2].x, ei = c[order - 2].y, orr = c[order - 1].x, oi = c[order - 1].y;
+    const C2 ct = c[n64 - 2], cu = c[n64 - 1];
+    double er = ct.x, ei = ct.y;
+    if (SEED) { er = fma(sr, wr, fma(-si, wi, ct.x)); ei = fma(sr, wi, fma(si, wr, ct.y)); }
+    double orr = cu.x, oi = cu.y;
+#if ONEKA_FF_PREFETCH
+    // software-pipelined: the coefficients of the next trip are loaded before the current trip's eight FMAs
+    if (n64 >= 4) {
+        C2 ce = c[n64 - 4], co = c[n64 - 3];
 #pragma unroll 2
-    for (int k = order - 4; k >= 0; k -= 2) {
+        for (int k = n64 - 4; k >= 2; k -= 2) {
+            const C2 ne = c[k - 2], no = c[k - 1];
+            const double ner = fma(er, wr, fma(-ei, wi, ce.x));
+            const double nei = fma(er, wi, fma(ei, wr, ce.y));
+            const double nor = fma(orr, wr, fma(-oi, wi, co.x));
+            const double noi = fma(orr, wi, fma(oi, wr, co.y));
+            er = ner; ei = nei; orr = nor; oi = noi;
+            ce = ne; co = no;
+        }
+        const double ner = fma(er, wr, fma(-ei, wi, ce.x));
+        const double nei = fma(er, wi, fma(ei, wr, ce.y));
+        const double nor = fma(orr, wr, fma(-oi, wi, co.x));
+        const double noi = fma(orr, wi, fma(oi, wr, co.y));
+        er = ner; ei = nei; orr = nor; oi = noi;
+    }
+#else
+#pragma unroll 2
+    for (int k = n64 - 4; k >= 0; k -= 2) {
         const C2 ce = c[k], co = c[k + 1];
         const double ner = fma(er, wr, fma(-ei, wi, ce.x));
         const double nei = fma(er, wi, fma(ei, wr, ce.y));
@@ -385,20 +449,45 @@ __host__ __device__ __forceinline__ void ff_poly_eval(const C2 *c, int order, do
         const double noi = fma(orr, wi, fma(oi, wr, co.y));
         er = ner; ei = nei; orr = nor; oi = noi;
     }
+#endif
     re = fma(orr, zr, fma(-oi, zi, er));
     im = fma(orr, zi, fma(oi, zr, ei));
 }
 
-// tile of the point (dx0, dy0) [relative to (xo, yo)] and its scaled offset from the tile centre; false = outside the grid
+// tile of the point (dx0, dy0) [relative to (xo, yo)] and its scaled offset from the tile centre; false = outside the grid.
+// floor() by the 1.5 * 2^52 trick (no F2I / I2F of the quarter-rate conversion pipe): m = (u - 0.5) + MAGIC rounds to the
+// integer nearest u - 0.5, whose low word is the tile index.  On an exact tile boundary ties-to-even may pick either
+// neighbour; both expansions hold there (|zeta| <= 1 on the closed tile).
+__host__ __device__ __forceinline__ int ff_lo32(double m)
+{
+#ifdef __CUDA_ARCH__
+    return __double2loint(m);
+#else
+    long long b;
+    memcpy(&b, &m, 8);
+    return (int)(unsigned int)(b & 0xffffffffLL);
+#endif
+}
 __host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0, double gy0, double inv_tile,
                                                    double dx0, double dy0, int &tile, double &zr, double &zi)
 {
-    const double tx = (dx0 - gx0) * inv_tile, ty = (dy0 - gy0) * inv_tile;
-    if (!(tx >= 0.0 && tx < (double)ntx && ty >= 0.0 && ty < (double)nty)) return false;      // also nan
-    const int ti = (int)tx, tj = (int)ty;                                                      // trunc = floor for tx >= 0
+    const double ux = (dx0 - gx0) * inv_tile, uy = (dy0 - gy0) * inv_tile;
+#if ONEKA_FF_LOCATE_CVT
+    if (!(ux >= 0.0 && ux < (double)ntx && uy >= 0.0 && uy < (double)nty)) return false;      // also nan
+    const int ci = (int)ux, cj = (int)uy;                                                      // trunc = floor for u >= 0
+    tile = cj * ntx + ci;
+    zr = (ux - (double)ci - 0.5) * FF_SQRT2;
+    zi = (uy - (double)cj - 0.5) * FF_SQRT2;
+    return true;
+#endif
+    constexpr double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
+    if (!(fabs(ux) < 1e9 && fabs(uy) < 1e9)) return false;                 // far away or nan: the trick needs |u| < 2^31
+    const double mx = (ux - 0.5) + MAGIC, my = (uy - 0.5) + MAGIC;
+    const int ti = ff_lo32(mx), tj = ff_lo32(my);
+    if ((unsigned int)ti >= (unsigned int)ntx || (unsigned int)tj >= (unsigned int)nty) return false;
     tile = tj * ntx + ti;
-    zr = (tx - (double)ti - 0.5) * FF_SQRT2;                                                   // (x - x_c)/h,  h = tile/sqrt 2
-    zi = (ty - (double)tj - 0.5) * FF_SQRT2;
+    zr = fma(ux - (mx - MAGIC), FF_SQRT2, -0.5 * FF_SQRT2);                // (x - x_c)/h,  h = tile/sqrt 2
+    zi = fma(uy - (my - MAGIC), FF_SQRT2, -0.5 * FF_SQRT2);
     return true;
 }
 
@@ -423,20 +512,26 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     }
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
+    // far wells, high orders: FP32
+    float tr = 0.0f, ti = 0.0f;
+#if ONEKA_FF_TAIL
+    if (ff.n32 > 0) ff_tail_eval(fs.c32 + tile * ff.n32, ff.n32, (float)zr, (float)zi, tr, ti);
+#endif
     // near wells, two per trip (lists are padded to even length with the dummy well, whose term is ~1e-100)
-    const unsigned short *po = fs.off + tile * ff.max_near;
+    const unsigned int *po = fs.off + tile * ff.max_near;
     const int n = fs.cnt[tile];
+    const char *sw = reinterpret_cast<const char *>(s_wells);
     double hx = 0.0, hy = 0.0;                                   // second accumulator pair: two independent chains
 #pragma unroll 1
     for (int i = 0; i < n; i += 2) {
-        const unsigned int o2 = *reinterpret_cast<const unsigned int *>(po + i);
-        const double *p0 = s_wells + (o2 & 0xffffu), *p1 = s_wells + (o2 >> 16);
+        const uint2 o2 = *reinterpret_cast<const uint2 *>(po + i);
+        const double *p0 = reinterpret_cast<const double *>(sw + o2.x), *p1 = reinterpret_cast<const double *>(sw + o2.y);
         scaled_term(dx0, dy0, p0[0], p0[1], p0[2], gx, gy);
         scaled_term(dx0, dy0, p1[0], p1[1], p1[2], hx, hy);
     }
-    // far wells: one polynomial
+    // far wells, low orders: FP64, seeded with the tail
     double re, im;
-    ff_poly_eval(fs.coef + tile * ff.order, ff.order, zr, zi, re, im);
+    ff_poly_eval<ONEKA_FF_TAIL != 0>(fs.c64 + tile * ff.n64, ff.n64, zr, zi, (double)tr, (double)ti, re, im);
     fx = (gx + hx) + re;
     fy = (gy + hy) - im;
     return PATH_OK;

@@ -156,6 +156,7 @@ class Engine:
         self.farfield_order = int(os.environ.get("ONEKA_FARFIELD_ORDER", "28"))
         self.farfield_eta = float(os.environ.get("ONEKA_FARFIELD_ETA", "0.3"))
         self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "64"))
+        self.farfield_order_fp64 = int(os.environ.get("ONEKA_FARFIELD_FP64", "0"))      # 0 = automatic FP64 / FP32 split
         self.farfield_min_wells = 12
         self._ff_key = None
         self._ff_info = None
@@ -214,7 +215,7 @@ class Engine:
         covering box = (xmin, xmax, ymin, ymax).  Returns dict(tile, ntx, nty, order, eta, mean_near, max_near)."""
         if spec is None or box is None:
             if self._ff_key is not None:
-                _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, None, None))
+                _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, 0, None, None))
             self._ff_key, self._ff_info = None, None
             return None
         order = int(order or self.farfield_order)
@@ -224,7 +225,7 @@ class Engine:
         mx, mean = C.c_int32(0), C.c_double(0.0)
         _cabi.check(self._L.oneka_set_farfield(self._h, len(wxy), wxy.ctypes.data, float(spec.xtarget), float(spec.ytarget),
                                                g["x0"], g["y0"], g["tile"], g["ntx"], g["nty"], order, eta,
-                                               C.byref(mx), C.byref(mean)))
+                                               int(self.farfield_order_fp64), C.byref(mx), C.byref(mean)))
         info = dict(g, order=order, eta=eta, mean_near=mean.value, max_near=int(mx.value))
         self._ff_key = (self._ff_wells_key(spec), tuple(float(v) for v in box))
         self._ff_info = info
@@ -256,7 +257,7 @@ class Engine:
         # cost model in well-equivalents (8 FP64 + loads per well): a near well ~1.3, a polynomial term ~0.55
         cost = 1.3 * (info["mean_near"] + 1.0) + 0.55 * info["order"] + 2.0
         if cost >= 0.85 * nw:                                       # not worth it: drop the tables, remember the decision
-            _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, None, None))
+            _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, 0, None, None))
             self._ff_key, self._ff_info = key, None
 
     def farfield_info(self):

@@ -19,13 +19,13 @@ def _field(name):
     return wxy, q / (2 * np.pi * 20.0 * 0.25), float(xo), float(yo)
 
 
-def _eval(wxy, w, xo, yo, grid, order, eta, pts):
+def _eval(wxy, w, xo, yo, grid, order, eta, pts, fp64=0):
     L = _cabi.load()
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     out = np.zeros((len(pts), 2))
     near = np.zeros(len(pts), dtype=np.int32)
     _cabi.check(L.oneka_farfield_eval_host(len(wxy), wxy.ctypes.data, w.ctypes.data, xo, yo, grid["x0"], grid["y0"],
-                                           grid["tile"], grid["ntx"], grid["nty"], order, eta, len(pts),
+                                           grid["tile"], grid["ntx"], grid["nty"], order, eta, fp64, len(pts),
                                            pts.ctypes.data, out.ctypes.data, near.ctypes.data))
     return out, near
 
@@ -109,5 +109,5 @@ def test_bad_arguments():
     pts, out = np.zeros((1, 2)), np.zeros((1, 2))
     for order, eta, ntx in [(27, 0.3, 4), (2, 0.3, 4), (28, 0.95, 4), (28, 0.3, 0), (28, 0.3, 5000)]:
         rc = L.oneka_farfield_eval_host(len(wxy), wxy.ctypes.data, w.ctypes.data, xo, yo, 0.0, 0.0, 100.0, ntx, 4, order, eta,
-                                        1, pts.ctypes.data, out.ctypes.data, None)
+                                        0, 1, pts.ctypes.data, out.ctypes.data, None)
         assert rc == -1 and b"far field" in L.oneka_last_error()
