@@ -260,6 +260,33 @@ class Engine:
             _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, 0, None, None))
             self._ff_key, self._ff_info = key, None
 
+    def _farfield_from_pilot(self, spec: FlowSpec, params: RealizationParams, dp: DeviceParams, pilot=64, pilot_paths=64,
+                             margin=0.25):
+        """Tracking-only passes have no lattice to take the tile grid from (run_exact's bounding-box pass is a FULL
+        tracking pass): when the far field would apply and no tables for these wells exist yet, a small strided pilot
+        (direct sums, <= pilot x pilot_paths particles) estimates the extents and the tables are built on them.  A
+        particle that leaves the estimate takes the direct sum, so a poor estimate only costs time."""
+        R = len(params)
+        if (self.farfield == "off" or not spec.confined or len(spec.well_xy) < self.farfield_min_wells or R == 0
+                or (self._ff_key is not None and self._ff_key[0] == self._ff_wells_key(spec))):
+            return
+        start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        rstep = max(1, R // max(1, pilot))
+        pstep = max(1, spec.npaths // max(1, pilot_paths))
+        self.reset_stats()
+        if rstep == 1 and pstep == 1:
+            self.capture(spec, dp)
+        else:
+            self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
+        bbox = self.read_stats()["bbox"]
+        if not np.all(np.isfinite(bbox)):
+            return
+        w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+        pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
+        est = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
+            bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+        self._auto_farfield(spec, est)
+
     def farfield_info(self):
         """The active far-field configuration (None = direct sums)."""
         return self._ff_info
@@ -426,6 +453,7 @@ class Engine:
         dp = self.upload(spec, params)
         if base is None:
             base = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget)
+        self._farfield_from_pilot(spec, params, dp)
         self.reset_stats()
         bb = self.path_bboxes(spec, dp)
         st = self.read_stats()
