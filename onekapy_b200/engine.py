@@ -235,10 +235,12 @@ class Engine:
         return (len(spec.well_xy), float(spec.xtarget), float(spec.ytarget),
                 np.ascontiguousarray(spec.well_xy, dtype=np.float64).tobytes())
 
-    def _auto_farfield(self, spec: FlowSpec, geom: Optional[LatticeGeom]):
+    def _auto_farfield(self, spec: FlowSpec, geom: Optional[LatticeGeom], box=None):
         """Called before every capture: keep / build / drop the far-field tables for this spec and lattice.
         Tracking-only calls (geom None) keep tables built for the same wells (a particle outside the tile grid takes
-        the direct sum anyway) and otherwise run direct."""
+        the direct sum anyway) and otherwise run direct.  `box` = (xmin, xmax, ymin, ymax) where the particles are
+        expected, when that is known to be tighter than the lattice (Engine.run's work lattice carries a 25 % safety
+        margin per side; tiles sized for it would be 1.5x larger and their near lists twice as long)."""
         nw = len(spec.well_xy)
         if self.farfield == "off" or not spec.confined or nw < self.farfield_min_wells:
             if self._ff_key is not None:
@@ -249,7 +251,9 @@ class Engine:
             if self._ff_key is not None and self._ff_key[0] != wkey:
                 self.set_farfield(None)
             return
-        box = tuple(float(v) for v in (geom.xmin, geom.xmax, geom.ymin, geom.ymax))
+        if box is None:
+            box = (geom.xmin, geom.xmax, geom.ymin, geom.ymax)
+        box = tuple(float(v) for v in box)
         key = (wkey, box)
         if self._ff_key == key:
             return
@@ -368,7 +372,7 @@ class Engine:
         return self.torch.zeros((geom.nrows, geom.ncols), dtype=self.torch.int32, device=self.device)
 
     def capture(self, spec: FlowSpec, dp: DeviceParams, geom: Optional[LatticeGeom] = None, counts=None,
-                per_path=False, r0=0, r1=None, clip=None, flags=None):
+                per_path=False, r0=0, r1=None, clip=None, flags=None, ff_box=None):
         """Enqueue track + rasterise + register for realizations [r0, r1) of `dp` (asynchronous).
 
         geom/counts None -> tracking only.  clip: int32 device tensor [R, P, 4] of per-path raster windows
@@ -384,7 +388,7 @@ class Engine:
             status = torch.zeros((R, P), dtype=torch.uint8, device=self.device)
         m = spec.model_desc()
         lat = geom.as_lattice(spec.umbra) if geom is not None else None
-        self._auto_farfield(spec, geom)
+        self._auto_farfield(spec, geom, ff_box)
         nvtx = self.torch.cuda.nvtx if os.environ.get("ONEKA_NVTX") else None      # ranges for nsys / ncu --nvtx
         if nvtx:
             nvtx.range_push("oneka.capture R=%d P=%d %s" % (R, P, "track+raster" if lat is not None else "track"))
@@ -573,7 +577,7 @@ class Engine:
             return self._empty_result(spec)              # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
         # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
         if hint is not None:
-            geom = hint
+            geom, ff_box = hint
         else:
             bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, dev)
             if not np.all(np.isfinite(bbox)):
@@ -582,11 +586,13 @@ class Engine:
             pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
             geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
                 bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+            # far-field tiles cover where the particles are (pilot box + 10 %), not the lattice's safety margin
+            ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
         work_geom = geom
         counts = self.new_counts(geom)
         flags = self.torch.zeros(R, dtype=self.torch.int32, device=self.device)
         self.reset_stats()
-        pp = self.capture(spec, dp, geom, counts, per_path=per_path, flags=flags)
+        pp = self.capture(spec, dp, geom, counts, per_path=per_path, flags=flags, ff_box=ff_box)
         stats = self.read_stats()
         true_bbox = parallel.reduce_bbox(stats["bbox"], group, dev)
         nflag = int(flags.sum().item()) if R else 0
@@ -598,7 +604,7 @@ class Engine:
             counts2 = self.new_counts(final)
             _copy_overlap(counts, geom, counts2, final)
             if nflag:
-                self.capture(spec, dp.select(flags.nonzero().reshape(-1)), final, counts2)
+                self.capture(spec, dp.select(flags.nonzero().reshape(-1)), final, counts2, ff_box=ff_box)
             counts, geom = counts2, final
         elif not geom.strictly_contains(true_bbox):
             raise OnekaError("internal: a vertex left the lattice but no realization was flagged")
@@ -613,7 +619,7 @@ class Engine:
         if per_path:
             pp = {k: _to_host(v) for k, v in pp.items()}
         if reuse_lattice and not rerun:
-            self._geom_hint[key] = work_geom             # it fitted every realization: a good estimate for the next call
+            self._geom_hint[key] = (work_geom, ff_box)   # it fitted every realization: a good estimate for the next call
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
 
 

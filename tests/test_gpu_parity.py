@@ -415,7 +415,7 @@ def test_run_with_subsampled_pilot(eng, golden):
     short.duration = spec.duration / 4
     small = eng.run(short, par)["work_geom"]
     key_dur = [k for k in eng._geom_hint if k[4] == short.duration][0]
-    eng._geom_hint[tuple(spec.duration if i == 4 else v for i, v in enumerate(key_dur))] = small
+    eng._geom_hint[tuple(spec.duration if i == 4 else v for i, v in enumerate(key_dur))] = (small, None)
     f = eng.run(spec, par)
     assert f["stats"]["rerun_realizations"] > 0 and f["geom"] == a["geom"] and np.array_equal(f["counts"], a["counts"])
     for r in (b, c):
