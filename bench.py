@@ -343,7 +343,9 @@ def run_ours(args):
     nominal = 148 * 64 * 2 * (sampler.max_mhz or 1965) * 1e6 / 1e12
     # DRAM traffic of the fused kernel from the ncu --set full capture in profiles/ (27.9 MB per 1000 realizations of
     # the perham field, dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch: the path is not HBM-bound
-    traffic = 27.9e6 * (R / 1000.0) if args.workload == "c3" else None
+    # (far field on: 75.1 MB per 1000 realizations, profiles/r01_track_kernel_farfield_raw.csv -- the 28 KB coefficient
+    # table of each realization and more bitmap write-back; still 0.05 % of the HBM peak)
+    traffic = (75.1e6 if ff_info else 27.9e6) * (R / 1000.0) if args.workload == "c3" else None
     # with the far-field compression the kernel EXECUTES fewer flops than the reference's formulation needs: per evaluation
     # 20 (regional) + 16 per near well + 8 per polynomial term + ~16 of tile lookup, FMA = 2 (estimate from the mean near count)
     if ff_info:
@@ -353,7 +355,7 @@ def run_ours(args):
     roofline = {"bound": "fp64", "kernel": "track_kernel<confined, raster%s>" % (", far field" if ff_info else ""),
                 "achieved": achieved, "peak": probe_tf,
                 "unit": "TFLOP/s", "frac": achieved / probe_tf, "traffic": traffic,
-                "traffic_note": "bytes per launch scaled from profiles/r01_track_kernel_raw.csv (ncu --set full at R=1000); HBM is idle (0.01 % of peak), the bound is the FP64 pipe",
+                "traffic_note": "bytes per launch scaled from profiles/r01_track_kernel%s_raw.csv (ncu --set full at R=1000); HBM is idle (< 0.1 %% of peak), the bound is the FP64 pipe / issue port" % ("_farfield" if ff_info else ""),
                 "peak_source": "in-run DFMA probe (oneka_fp64_probe); MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x max clock = %.1f" % nominal,
                 "flops_per_attempt": flops_per_attempt(nw), "attempts_per_launch": att_per_launch, "kernel_ms_per_launch": track_ms,
                 "flops_executed_per_attempt_estimate": exec_flops, "frac_executed_estimate": achieved * exec_flops / flops_per_attempt(nw) / probe_tf,

@@ -111,3 +111,12 @@ def test_bad_arguments():
         rc = L.oneka_farfield_eval_host(len(wxy), wxy.ctypes.data, w.ctypes.data, xo, yo, 0.0, 0.0, 100.0, ntx, 4, order, eta,
                                         0, 1, pts.ctypes.data, out.ctypes.data, None)
         assert rc == -1 and b"far field" in L.oneka_last_error()
+
+
+def test_farfield_grid_covers_the_box():
+    for box, max_tiles in [((0.0, 2800.0, 0.0, 2400.0), 64), ((300000.0, 303900.0, 5160000.0, 5161800.0), 64),
+                           ((0.0, 300.0, 0.0, 200.0), 64), ((0.0, 17000.0, 0.0, 13000.0), 16), ((5.0, 5.0, 7.0, 7.0), 64)]:
+        g = farfield_grid(box, max_tiles)
+        assert 1 <= g["ntx"] * g["nty"] <= max_tiles and g["tile"] >= 100.0
+        assert g["x0"] <= box[0] and g["x0"] + g["ntx"] * g["tile"] >= box[1]
+        assert g["y0"] <= box[2] and g["y0"] + g["nty"] * g["tile"] >= box[3]
