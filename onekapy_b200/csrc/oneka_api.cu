@@ -154,17 +154,23 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
     FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
     if (FF) {
         const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
+        const double2 *g = ff.coef + (size_t)r * ntiles * order;
+#if ONEKA_FF_COEF_GLOBAL
+        const double2 *s_c64 = g;                                // read in place through L1 (all-FP64 builds only)
+        float2 *s_c32 = nullptr;
+        unsigned int *s_off = reinterpret_cast<unsigned int *>(s_dyn + ff_store_double2(tp.nw));
+#else
         double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
         float2 *s_c32 = reinterpret_cast<float2 *>(s_c64 + ntiles * ff.n64);
         unsigned int *s_off = reinterpret_cast<unsigned int *>(s_c32 + ntiles * ff.n32);
-        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
-        const double2 *g = ff.coef + (size_t)r * ntiles * order;
         for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) {          // coalesced read of the realization's table
             const int t = i / order, k = i - t * order;
             const double2 c = g[i];
             if (k < ff.n64) s_c64[t * ff.n64 + k] = c;
             else s_c32[t * ff.n32 + (k - ff.n64)] = make_float2((float)c.x, (float)c.y);
         }
+#endif
+        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
         for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_off[i] = ff.near_off[i];
         for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = ff.near_cnt[i];
         if (threadIdx.x == 0) {                                  // the dummy well that pads odd near lists: term ~1e-100
@@ -449,7 +455,11 @@ static void prof_end(oneka_ctx *ctx)
 static size_t ff_smem(const FarFieldDev &ff)
 {
     const size_t nt = (size_t)ff.ntx * ff.nty;
+#if ONEKA_FF_COEF_GLOBAL
+    return (nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
+#else
     return (nt * ff.n64 * sizeof(double2) + nt * ff.n32 * sizeof(float2) + nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
+#endif
 }
 
 template <int MODE>
@@ -579,6 +589,9 @@ struct FFTables {
 // terms kept in FP64: the smallest even k with eta^k <= 2^-24 (see ff_tail_eval), at most `order`
 static int ff_split(int order, double eta, int order_fp64)
 {
+#if ONEKA_FF_TAIL && ONEKA_FF_COEF_GLOBAL
+#error "ONEKA_FF_COEF_GLOBAL reads double2 coefficients in place: it excludes the FP32 tail"
+#endif
 #if !ONEKA_FF_TAIL
     (void)eta; (void)order_fp64;
     return order;                               // this build evaluates every term in FP64

@@ -389,6 +389,12 @@ constexpr double FF_SQRT2 = 1.4142135623730951;
 #ifndef ONEKA_FF_PREFETCH
 #define ONEKA_FF_PREFETCH 0
 #endif
+// ONEKA_FF_COEF_GLOBAL 1 (NOT yet timed on hardware -- prepared for the next round): the coefficient tables stay in global
+// memory and are read through L1 (ld.global.nc); shared memory then holds only the near lists, so the tile count is no longer
+// bounded by it (256 tiles of ~110 m: ~0.7 near wells per evaluation at C3 instead of 2, and a lower order suffices).
+#ifndef ONEKA_FF_COEF_GLOBAL
+#define ONEKA_FF_COEF_GLOBAL 0
+#endif
 // THE FP32 TAIL (ONEKA_FF_TAIL).  |c_k| <= S eta^k (S = sum over the far wells of |w|/|z_w - z_c|), so the terms k >= n64 with
 // eta^n64 <= 2^-24 contribute at most 2^-24 S: evaluated in FP32 (FFMA: half the issue cost of DFMA, on the otherwise idle
 // FP32 pipe) their rounding error is ~2^-23 x 2^-24 S = 7e-15 S, the level of the truncation itself.
@@ -409,10 +415,12 @@ __host__ __device__ __forceinline__ void ff_tail_eval(const F2 *t, int n, float 
 
 // sum_{k < n64} c_k zeta^k + zeta^n64 (sr + i si): two interleaved Horner chains in w = zeta^2 (even / odd powers, half the
 // dependency depth); the tail value seeds the even chain as the coefficient of w^(n64/2)
-template <bool SEED, typename C2>
-__host__ __device__ __forceinline__ void ff_poly_eval(const C2 *c, int n64, double zr, double zi, double sr, double si,
+// `c` is anything indexable that yields {x, y}: a pointer to double2, or CoefLdg (read-only global loads through L1)
+template <bool SEED, typename CP>
+__host__ __device__ __forceinline__ void ff_poly_eval(CP c, int n64, double zr, double zi, double sr, double si,
                                                       double &re, double &im)
 {
+    typedef double2 C2;
     const double wr = fma(zr, zr, -(zi * zi));
     const double wi = 2.0 * (zr * zi);
     const C2 ct = c[n64 - 2], cu = c[n64 - 1];
@@ -492,6 +500,10 @@ __host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0,
 }
 
 #ifdef __CUDACC__
+struct CoefLdg {
+    const double2 *p;
+    __device__ __forceinline__ double2 operator[](int k) const { return __ldg(p + k); }
+};
 // the direct sum as an out-of-line call: the rare particle outside the tile grid
 __device__ __noinline__ void field_direct_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
 {
@@ -531,7 +543,11 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     }
     // far wells, low orders: FP64, seeded with the tail
     double re, im;
+#if ONEKA_FF_COEF_GLOBAL
+    ff_poly_eval<ONEKA_FF_TAIL != 0>(CoefLdg{fs.c64 + tile * ff.n64}, ff.n64, zr, zi, (double)tr, (double)ti, re, im);
+#else
     ff_poly_eval<ONEKA_FF_TAIL != 0>(fs.c64 + tile * ff.n64, ff.n64, zr, zi, (double)tr, (double)ti, re, im);
+#endif
     fx = (gx + hx) + re;
     fy = (gy + hy) - im;
     return PATH_OK;
