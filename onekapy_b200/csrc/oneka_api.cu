@@ -153,16 +153,19 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
     FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
     if (FF) {
-        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
-        const double2 *g = ff.coef + (size_t)r * ntiles * order;
 #if ONEKA_FF_COEF_GLOBAL
-        const double2 *s_c64 = g;                                // read in place through L1 (all-FP64 builds only)
+        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
+        const double2 *s_c64 = ff.coef + (size_t)r * ntiles * order;             // read in place through L1 (all-FP64 builds only)
         float2 *s_c32 = nullptr;
         unsigned int *s_off = reinterpret_cast<unsigned int *>(s_dyn + ff_store_double2(tp.nw));
+        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
 #else
+        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
         double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
         float2 *s_c32 = reinterpret_cast<float2 *>(s_c64 + ntiles * ff.n64);
         unsigned int *s_off = reinterpret_cast<unsigned int *>(s_c32 + ntiles * ff.n32);
+        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
+        const double2 *g = ff.coef + (size_t)r * ntiles * order;
         for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) {          // coalesced read of the realization's table
             const int t = i / order, k = i - t * order;
             const double2 c = g[i];
@@ -170,7 +173,6 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
             else s_c32[t * ff.n32 + (k - ff.n64)] = make_float2((float)c.x, (float)c.y);
         }
 #endif
-        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
         for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_off[i] = ff.near_off[i];
         for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = ff.near_cnt[i];
         if (threadIdx.x == 0) {                                  // the dummy well that pads odd near lists: term ~1e-100
