@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC \
 //        -Iinclude onekapy_b200/csrc/oneka_api.cu -o onekapy_b200/liboneka_b200.so
 #include "oneka_device.cuh"
+#include "oneka_farfield_host.h"
 #include "../../include/oneka_b200.h"
 
 #include <cstdio>
@@ -79,61 +80,7 @@ struct oneka_ctx {
 // ------------------------------------------------------------------------------------------
 // Kernels
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double cf_F(const TrackParams &tp, long long r) { return tp.coef[6 * r + 5]; }
-
-template <bool CONFINED>
-__device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc, double *s_wells)
-{
-    const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
-    const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
-    if (CONFINED) {                                                                  // layout: oneka_device.cuh, SWELL_BLK
-        for (int j = threadIdx.x; j < ((tp.nw + 3) & ~3); j += blockDim.x) {
-            double b = 0.0, cx = 0.0, cy = 0.0;
-            if (j < tp.nw) {
-                const int i = j;
-                const double w = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;    // q/(2 pi H n)
-                b = (w != 0.0) ? 1.0 / w : 1e100;                                    // q = 0: the term becomes ~1e-100, i.e. nothing
-                cx = -(tp.well_xy[2 * i] - tp.xo) * b;
-                cy = -(tp.well_xy[2 * i + 1] - tp.yo) * b;
-            }
-            double *d = s_wells + (j >> 2) * SWELL_BLK + 3 * (j & 3);
-            d[0] = b; d[1] = cx; d[2] = cy;
-        }
-    } else {
-        for (int i = threadIdx.x; i < ((tp.nw + 3) & ~3); i += blockDim.x) {        // layout: oneka_device.cuh, WELL_BLK
-            const bool real = i < tp.nw;
-            const double w = real ? tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 : 0.0;    // q/(2 pi)
-            well_x(s_wells, i) = real ? tp.well_xy[2 * i] : 0.0;
-            well_y(s_wells, i) = real ? tp.well_xy[2 * i + 1] : 0.0;
-            well_w(s_wells, i) = w;
-            well_w32(s_wells, i) = (float)w;
-        }
-    }
-    if (threadIdx.x == 0) {
-        const double *cf = tp.coef + 6 * r;
-        rc.a2 = 2.0 * cf[0] * scale;
-        rc.b2 = 2.0 * cf[1] * scale;
-        rc.c = cf[2] * scale;
-        rc.d = cf[3] * scale;
-        rc.e = cf[4] * scale;
-        rc.A = cf[0]; rc.B = cf[1]; rc.F = cf[5];
-        rc.k = k; rc.H = H; rc.n = n;
-        rc.half_kH2 = 0.5 * k * (H * H);
-        rc.inv_Hn = 1.0 / (H * n);
-        rc.xo = tp.xo; rc.yo = tp.yo;
-    }
-    __syncthreads();
-    if (!CONFINED) {
-        // error bound of the FP32 screening sum: per term <= |w| (47 * 2^-23 * 2 + 2^-22) log2 units, accumulation
-        // <= nw * 2^-24 * 47 sum|w|; times 0.5 ln 2, with a 5x margin:  2e-5 (nw + 16) sum|w|
-        if (threadIdx.x == 0) {
-            double sw = 0.0;
-            for (int i = 0; i < tp.nw; ++i) sw += fabs(well_w(s_wells, i));
-            rc.pot_err = 2e-5 * (double)(tp.nw + 16) * sw + 1e-9 * fabs(cf_F(tp, r));
-        }
-        __syncthreads();
-    }
-}
+// stage_realization<CONFINED> (the per-CTA well store and realization constants) lives in oneka_device.cuh
 
 // One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
 // FF (confined only): the realization's far-field coefficient table and the tiles' near lists are staged behind the
@@ -577,90 +524,6 @@ static double undkey(unsigned long long k)
 }
 
 // ------------------------------------------------------------------------------------------
-// Far-field tables (host): geometry only -- see "Far-field compression" in oneka_device.cuh
-// ------------------------------------------------------------------------------------------
-struct FFTables {
-    int ntiles = 0, max_near = 0;
-    double mean_near = 0.0;
-    std::vector<double2> P;                    // [ntiles][nw][order]; zero rows for near wells
-    std::vector<unsigned int> off;             // [ntiles][max_near] byte offsets into the well store (padded with the dummy well)
-    std::vector<unsigned short> cnt;           // [ntiles] padded (even) lengths
-    std::vector<int> near_flat, near_begin;    // unpadded near lists (host evaluator)
-};
-
-// terms kept in FP64: the smallest even k with eta^k <= 2^-24 (see ff_tail_eval), at most `order`
-static int ff_split(int order, double eta, int order_fp64)
-{
-#if ONEKA_FF_TAIL && ONEKA_FF_COEF_GLOBAL
-#error "ONEKA_FF_COEF_GLOBAL reads double2 coefficients in place: it excludes the FP32 tail"
-#endif
-#if !ONEKA_FF_TAIL
-    (void)eta; (void)order_fp64;
-    return order;                               // this build evaluates every term in FP64
-#endif
-    if (order_fp64 > 0) { int k = (order_fp64 + 1) & ~1; return k < 2 ? 2 : (k > order ? order : k); }
-    int k = 2;
-    while (k < order && pow(eta, (double)k) > 5.9604644775390625e-08) k += 2;
-    return k > order ? order : k;
-}
-
-static int build_ff_tables(int nw, const double *well_xy, double xo, double yo, double gx0, double gy0, double tile,
-                           int ntx, int nty, int order, double eta, FFTables &T)
-{
-    if (nw < 1 || !well_xy) return fail(ONEKA_ERR_ARG, "far field needs nw >= 1 wells");
-    if (!(tile > 0.0) || ntx < 1 || nty < 1 || (long long)ntx * nty > 4096) return fail(ONEKA_ERR_ARG, "far field: bad tile grid %d x %d, tile %g", ntx, nty, tile);
-    if (order < 4 || order > 64 || (order & 1)) return fail(ONEKA_ERR_ARG, "far field: order must be even and in [4, 64]");
-    if (!(eta > 0.0 && eta < 0.9)) return fail(ONEKA_ERR_ARG, "far field: eta must be in (0, 0.9)");
-    const int ntiles = ntx * nty;
-    const long double h = (long double)tile / sqrtl(2.0L);
-    const long double rfar = h / (long double)eta;
-    T.ntiles = ntiles;
-    T.P.assign((size_t)ntiles * nw * order, make_double2(0.0, 0.0));
-    T.near_flat.clear();
-    T.near_begin.assign(ntiles + 1, 0);
-    int maxn = 0;
-    for (int tj = 0; tj < nty; ++tj)
-        for (int ti = 0; ti < ntx; ++ti) {
-            const int t = tj * ntx + ti;
-            const long double cx = (long double)gx0 + ((long double)ti + 0.5L) * tile;     // tile centre relative to (xo, yo)
-            const long double cy = (long double)gy0 + ((long double)tj + 0.5L) * tile;
-            for (int w = 0; w < nw; ++w) {
-                const long double dx = ((long double)well_xy[2 * w] - xo) - cx, dy = ((long double)well_xy[2 * w + 1] - yo) - cy;
-                const long double d2 = dx * dx + dy * dy;
-                if (!(sqrtl(d2) >= rfar)) { T.near_flat.push_back(w); continue; }          // near (or nan): summed directly
-                const long double ir = dx / d2, ii = -dy / d2;                              // 1/(z_w - z_c)
-                const long double ur = h * ir, ui = h * ii;                                 // h/(z_w - z_c)
-                long double tr = -ir, tim = -ii;                                            // term_0 = -1/(z_w - z_c)
-                double2 *row = &T.P[((size_t)t * nw + w) * order];
-                for (int k = 0; k < order; ++k) {
-                    row[k] = make_double2((double)tr, (double)tim);
-                    const long double nr = tr * ur - tim * ui, ni = tr * ui + tim * ur;
-                    tr = nr; tim = ni;
-                }
-            }
-            T.near_begin[t + 1] = (int)T.near_flat.size();
-            const int n = T.near_begin[t + 1] - T.near_begin[t];
-            if (n > maxn) maxn = n;
-        }
-    T.max_near = (maxn + 1) & ~1;
-    if (T.max_near < 2) T.max_near = 2;
-    T.mean_near = (double)T.near_flat.size() / ntiles;
-    if (T.max_near > 65534) return fail(ONEKA_ERR_ARG, "far field: near list too long");
-    const unsigned int dummy = (unsigned int)ff_dummy_offset(nw) * 8u;
-    T.off.assign((size_t)ntiles * T.max_near, dummy);
-    T.cnt.assign(ntiles, 0);
-    for (int t = 0; t < ntiles; ++t) {
-        const int n = T.near_begin[t + 1] - T.near_begin[t];
-        for (int i = 0; i < n; ++i) {
-            const int w = T.near_flat[T.near_begin[t] + i];
-            T.off[(size_t)t * T.max_near + i] = (unsigned int)((w >> 2) * SWELL_BLK + 3 * (w & 3)) * 8u;
-        }
-        T.cnt[t] = (unsigned short)((n + 1) & ~1);
-    }
-    return ONEKA_OK;
-}
-
-// ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -780,8 +643,8 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (f.near_cnt) { cudaFree(f.near_cnt); f.near_cnt = nullptr; }
     if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
     FFTables T;
-    int rc = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T);
-    if (rc) return rc;
+    if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
+        return fail(ONEKA_ERR_ARG, "%s", why);
     FarFieldDev probe;
     memset(&probe, 0, sizeof(probe));
     const int n64 = ff_split(order, eta, order_fp64);
@@ -808,20 +671,10 @@ int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const doubl
 {
     if (npts < 0 || !w_host || (npts && (!pts_host || !out_host))) return fail(ONEKA_ERR_ARG, "bad argument to oneka_farfield_eval_host");
     FFTables T;
-    int rc = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T);
-    if (rc) return rc;
-    // coefficients as farfield_coef_kernel forms them (w_host are the scaled discharges q/(2 pi H n))
-    std::vector<double2> coef((size_t)T.ntiles * order);
-    for (int t = 0; t < T.ntiles; ++t)
-        for (int k = 0; k < order; ++k) {
-            double ar = 0.0, ai = 0.0;
-            for (int w = 0; w < nw; ++w) {
-                const double2 pk = T.P[((size_t)t * nw + w) * order + k];
-                ar = fma(w_host[w], pk.x, ar);
-                ai = fma(w_host[w], pk.y, ai);
-            }
-            coef[(size_t)t * order + k] = make_double2(ar, ai);
-        }
+    if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
+        return fail(ONEKA_ERR_ARG, "%s", why);
+    std::vector<double2> coef;
+    ff_host_coefficients(T, nw, order, w_host, coef);
     // the split the device uses: low orders double2, the tail rounded to float2 (track_kernel's staging)
     const int n64 = ff_split(order, eta, order_fp64), n32 = order - n64;
     std::vector<float2> c32((size_t)T.ntiles * (n32 > 0 ? n32 : 1));

@@ -23,6 +23,35 @@
 namespace oneka {
 
 // ------------------------------------------------------------------------------------------
+// The approximate MUFU instructions the kernels use.  ONEKA_EMU (tests/emu: the device code compiled for the HOST to
+// unit-test kernel logic without a GPU -- test infrastructure, never part of the library) swaps in libm stand-ins;
+// every consumer already tolerates the difference (Newton step after the seed, error bands around the FP32 values).
+#ifdef ONEKA_EMU
+__device__ __forceinline__ double ptx_rcp_approx_f64(double a) { return 1.0 / a; }
+__device__ __forceinline__ float ptx_lg2_approx_f32(float a) { return log2f(a); }
+__device__ __forceinline__ float ptx_sqrt_approx_f32(float a) { return sqrtf(a); }
+#else
+__device__ __forceinline__ double ptx_rcp_approx_f64(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+}
+__device__ __forceinline__ float ptx_lg2_approx_f32(float a)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+__device__ __forceinline__ float ptx_sqrt_approx_f32(float a)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Status words (mirror include/oneka_b200.h)
 enum : int { PATH_OK = 0, PATH_AQUIFER_DRY = 1, PATH_MAX_ATTEMPT = 2, PATH_NONFINITE = 3, PATH_TRACE_FULL = 4 };
 
@@ -100,8 +129,7 @@ struct LatticeDev {
 // Relative error ~1 ulp; replaces the ~20-instruction IEEE divide in the well loop.
 __device__ __forceinline__ double rcp_fast(double a)
 {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double y = ptx_rcp_approx_f64(a);
     double e = fma(-a, y, 1.0);
     double t = fma(e, e, e);
     return fma(y, t, y);
@@ -118,7 +146,7 @@ __device__ __forceinline__ double rcp_fast(double a)
 #endif
 __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 {
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    y0 = ptx_rcp_approx_f64(a);
     double e = fma(-a, y0, 1.0);
 #if ONEKA_RCP_ORDER == 3
     t = fma(e, e, e);
@@ -180,8 +208,7 @@ __device__ __forceinline__ void well_term(double x, double y, double xw, double 
     gy = fma(s, dy, gy);
     // bare MUFU.LG2 (no denormal scaling: (float) r2 is a normal number for 1e-19 m < r < 1e19 m; outside, the
     // screening value is inf or nan and the comparison in field_feval sends a pumping well's neighbourhood to the FP64 path)
-    float l2;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"((float)r2));
+    const float l2 = ptx_lg2_approx_f32((float)r2);
     lsum32 = fmaf(w32, l2, lsum32);
 }
 
@@ -499,7 +526,7 @@ __host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0,
     return true;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(ONEKA_EMU)
 struct CoefLdg {
     const double2 *p;
     __device__ __forceinline__ double2 operator[](int k) const { return __ldg(p + k); }
@@ -611,9 +638,7 @@ struct ClipWin { int l, r, b, t; };
 // MUFU.SQRT (nan for negative arguments, as the callers expect)
 __device__ __forceinline__ float sqrt_fast(float a)
 {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-    return r;
+    return ptx_sqrt_approx_f32(a);
 }
 
 // Cold path.  `lat` = {xmin, ymin, dx, dy, umbra^2} in SHARED memory: were these taken from the kernel parameters,
@@ -989,6 +1014,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
     unsigned long long att = (unsigned long long)nattempt, stp = active ? (unsigned long long)(nvert - 1) : 0ull;
     unsigned int npath = active ? 1u : 0u, nbad = (active && status != PATH_OK) ? 1u : 0u;
     unsigned int ncl = ctr.clipped, nex = ctr.exact;
+#ifndef ONEKA_EMU                                             // (the emulation runs one lane per "warp")
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         att += __shfl_down_sync(0xffffffffu, att, o);
@@ -1002,6 +1028,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         by0 = fmin(by0, __shfl_down_sync(0xffffffffu, by0, o));
         by1 = fmax(by1, __shfl_down_sync(0xffffffffu, by1, o));
     }
+#endif
     if ((threadIdx.x & 31) == 0 && npath) {
         atomicAdd(tp.stats + STAT_ATTEMPTS, att);
         atomicAdd(tp.stats + STAT_STEPS, stp);
@@ -1013,6 +1040,65 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         atomicMax(tp.stats + STAT_XMAX, dkey(bx1));
         atomicMin(tp.stats + STAT_YMIN, dkey(by0));
         atomicMax(tp.stats + STAT_YMAX, dkey(by1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-CTA staging of one realization: the well store in shared memory + the realization constants
+// (called by every thread of the CTA; ends with a barrier)
+__device__ __forceinline__ double cf_F(const TrackParams &tp, long long r) { return tp.coef[6 * r + 5]; }
+
+template <bool CONFINED>
+__device__ __forceinline__ void stage_realization(const TrackParams &tp, long long r, RealConsts &rc, double *s_wells)
+{
+    const double H = tp.thick[r], n = tp.poro[r], k = tp.cond[r];
+    const double scale = CONFINED ? 1.0 / (H * n) : 1.0;
+    if (CONFINED) {                                                                  // layout: oneka_device.cuh, SWELL_BLK
+        for (int j = threadIdx.x; j < ((tp.nw + 3) & ~3); j += blockDim.x) {
+            double b = 0.0, cx = 0.0, cy = 0.0;
+            if (j < tp.nw) {
+                const int i = j;
+                const double w = tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 * scale;    // q/(2 pi H n)
+                b = (w != 0.0) ? 1.0 / w : 1e100;                                    // q = 0: the term becomes ~1e-100, i.e. nothing
+                cx = -(tp.well_xy[2 * i] - tp.xo) * b;
+                cy = -(tp.well_xy[2 * i + 1] - tp.yo) * b;
+            }
+            double *d = s_wells + (j >> 2) * SWELL_BLK + 3 * (j & 3);
+            d[0] = b; d[1] = cx; d[2] = cy;
+        }
+    } else {
+        for (int i = threadIdx.x; i < ((tp.nw + 3) & ~3); i += blockDim.x) {        // layout: oneka_device.cuh, WELL_BLK
+            const bool real = i < tp.nw;
+            const double w = real ? tp.q[(size_t)r * tp.nw + i] * 0.15915494309189535 : 0.0;    // q/(2 pi)
+            well_x(s_wells, i) = real ? tp.well_xy[2 * i] : 0.0;
+            well_y(s_wells, i) = real ? tp.well_xy[2 * i + 1] : 0.0;
+            well_w(s_wells, i) = w;
+            well_w32(s_wells, i) = (float)w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double *cf = tp.coef + 6 * r;
+        rc.a2 = 2.0 * cf[0] * scale;
+        rc.b2 = 2.0 * cf[1] * scale;
+        rc.c = cf[2] * scale;
+        rc.d = cf[3] * scale;
+        rc.e = cf[4] * scale;
+        rc.A = cf[0]; rc.B = cf[1]; rc.F = cf[5];
+        rc.k = k; rc.H = H; rc.n = n;
+        rc.half_kH2 = 0.5 * k * (H * H);
+        rc.inv_Hn = 1.0 / (H * n);
+        rc.xo = tp.xo; rc.yo = tp.yo;
+    }
+    __syncthreads();
+    if (!CONFINED) {
+        // error bound of the FP32 screening sum: per term <= |w| (47 * 2^-23 * 2 + 2^-22) log2 units, accumulation
+        // <= nw * 2^-24 * 47 sum|w|; times 0.5 ln 2, with a 5x margin:  2e-5 (nw + 16) sum|w|
+        if (threadIdx.x == 0) {
+            double sw = 0.0;
+            for (int i = 0; i < tp.nw; ++i) sw += fabs(well_w(s_wells, i));
+            rc.pot_err = 2e-5 * (double)(tp.nw + 16) * sw + 1e-9 * fabs(cf_F(tp, r));
+        }
+        __syncthreads();
     }
 }
 

@@ -1,0 +1,130 @@
+"""The LOGIC of the CUDA device code, run on the CPU: tests/emu compiles onekapy_b200/csrc/oneka_device.cuh for the host
+(one "thread" at a time, libm stand-ins for the MUFU approximations) and these tests hold it to the bars of the GPU parity
+tests -- against fixtures from the executed reference and against the oracle.  This is test infrastructure for working on the
+kernels without a GPU at hand; it is not a fallback (the package never sees it) and it does not replace `-m gpu`: launch
+code, shared-memory staging, warp reductions and contended atomics only exist on the device."""
+import numpy as np
+import pytest
+
+from helpers import scal, traces_of
+from emu import emu
+from onekapy_b200.engine import FlowSpec, RealizationParams, start_ring, farfield_grid
+from onekapy_b200.lattice import LatticeGeom
+
+CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz"]
+
+
+def spec_of(g):
+    s = scal(g)
+    spec = FlowSpec(well_xy=g["wells_xyr"][:, :2].copy(), xtarget=s["xt"], ytarget=s["yt"], rtarget=s["rt"],
+                    npaths=s["P"], duration=s["duration"], base=s["base"], spacing=s["spacing"], umbra=s["umbra"],
+                    confined=s["confined"], tol=s["tol"], maxstep=s["maxstep"])
+    par = RealizationParams(q=g["q"], cond=g["k"], poro=g["n"], thick=g["H"], coef=g["coef"])
+    return s, spec, par
+
+
+def fixed_geom(g, s):
+    return LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"]).expanded(*g["lattice"])
+
+
+def ff_box(g, spec, tiles=64, order=28, eta=0.3, shrink=0.0):
+    v = g["verts"]
+    x0, x1, y0, y1 = v[:, 0].min() - 50.0, v[:, 0].max() + 50.0, v[:, 1].min() - 50.0, v[:, 1].max() + 50.0
+    if shrink:
+        x1, y1 = x0 + (1 - shrink) * (x1 - x0), y0 + (1 - shrink) * (y1 - y0)
+    return dict(farfield_grid((x0, x1, y0, y1), tiles), order=order, eta=eta)
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_tracker_vs_executed_reference(golden, name):
+    """dopri_track + field_feval (MODE 2): the reference's vertices, step for step."""
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    out = emu.capture(spec, par, start_ring(s["xt"], s["yt"], s["rt"], s["P"]), 2, max_verts=1024)
+    worst = 0.0
+    for k, t in enumerate(traces_of(g)):
+        r, p = divmod(k, s["P"])
+        assert out["status"][r, p] == 0 and out["nverts"][r, p] == len(t), (name, r, p)
+        v = out["verts"][r, p, :len(t)]
+        worst = max(worst, (np.abs(v - t).max(axis=1) / np.maximum(np.abs(t).max(axis=1), 1.0)).max())
+    assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_fused_tracker_and_rasteriser_bit_exact(golden, name):
+    """dopri_track + raster_seg (MODE 1) + register: the executed reference's grid on the fixed lattice, cell for cell."""
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    out = emu.capture(spec, par, start_ring(s["xt"], s["yt"], s["rt"], s["P"]), 1, geom=gm)
+    tr = traces_of(g)
+    assert np.array_equal(out["nverts"].ravel(), [len(t) for t in tr])
+    assert out["stats"]["steps"] == sum(len(t) - 1 for t in tr) and out["stats"]["paths"] == len(tr)
+    assert np.array_equal(out["counts"], g["fixed_counts"].astype(np.uint32))
+    v = g["verts"]
+    assert np.allclose(out["stats"]["bbox"], [v[:, 0].min(), v[:, 0].max(), v[:, 1].min(), v[:, 1].max()], rtol=1e-9)
+
+
+@pytest.mark.parametrize("tiles,shrink", [(64, 0.0), (9, 0.0), (16, 0.5)])
+def test_far_field_evaluation_in_the_tracker(golden, tiles, shrink):
+    """field_feval_ff inside the tracker: same step sequence, same grid; shrink = 0.5 leaves three quarters of the
+    area to the direct-sum fallback."""
+    g = golden("sto_perham.npz")
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
+    ff = ff_box(g, spec, tiles, shrink=shrink)
+    direct = emu.capture(spec, par, ring, 2, max_verts=1024)
+    far = emu.capture(spec, par, ring, 2, max_verts=1024, farfield=ff)
+    assert np.array_equal(far["nverts"], direct["nverts"]) and np.array_equal(far["attempts"], direct["attempts"])
+    n = far["nverts"].max()
+    scale = np.maximum(np.abs(direct["verts"][:, :, :n]).max(axis=3), 1.0)
+    assert (np.abs(far["verts"][:, :, :n] - direct["verts"][:, :, :n]).max(axis=3) / scale).max() < 1e-12
+    fused = emu.capture(spec, par, ring, 1, geom=gm, farfield=ff)
+    assert np.array_equal(fused["counts"], g["fixed_counts"].astype(np.uint32))
+
+
+def test_far_field_200_wells_vs_direct():
+    import bench
+    spec, par, _ = bench.make_workload("c4", 2, 24, 11)
+    ring = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+    direct = emu.capture(spec, par, ring, 0)
+    bb = direct["stats"]["bbox"]
+    gm = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(*bb)
+    ff = dict(farfield_grid((gm.xmin, gm.xmax, gm.ymin, gm.ymax), 64), order=28, eta=0.3)
+    a = emu.capture(spec, par, ring, 1, geom=gm)
+    b = emu.capture(spec, par, ring, 1, geom=gm, farfield=ff)
+    assert a["stats"]["attempts"] == b["stats"]["attempts"] and np.array_equal(a["nverts"], b["nverts"])
+    assert np.array_equal(a["counts"], b["counts"]) and a["counts"].max() == 2
+    rel = np.abs(a["end_xy"] - b["end_xy"]).max() / np.abs(a["end_xy"]).max()
+    assert rel < 1e-12
+
+
+def test_rasteriser_insert_fixture_and_random_tracks(golden):
+    """raster_seg alone: hand-made tracks with exact ties (executed reference) and random tracks (oracle)."""
+    from oracle import oracle as O
+    g = golden("insert.npz")
+    tracks = traces_of(g)
+    for tag in "abc":
+        dx, dy, umbra = g["par_" + tag]
+        gm = LatticeGeom.anchored(dx, dy, 60.0, 60.0).expanded(0.0, 200.0, 0.0, 200.0)
+        counts, _ = emu.raster_traces(gm, umbra, tracks, g["real_of"], 2)
+        assert np.array_equal(counts, g["fixed_%s_counts" % tag].astype(np.uint32)), tag
+    rng = np.random.default_rng(4)
+    for dx, dy, umbra, step in [(4.0, 4.0, 8.0, 9.0), (2.5, 3.5, 11.0, 6.0), (10.0, 10.0, 4.0, 20.0), (1.0, 1.0, 7.3, 0.02)]:
+        gm = LatticeGeom.anchored(dx, dy, 13.7, -4.2).expanded(-150.0, 170.0, -140.0, 160.0)
+        tracks, cur = [], None
+        for _ in range(60):
+            n = int(rng.integers(2, 30))
+            ang = rng.uniform(0, 2 * np.pi) + np.cumsum(rng.normal(0, 0.3, n))
+            p = np.cumsum(np.stack([np.cos(ang), np.sin(ang)], axis=1) * step * rng.uniform(0.2, 1.0, (n, 1)), axis=0)
+            tracks.append(p + rng.uniform(-100, 100, 2))
+        counts, nexact = emu.raster_traces(gm, umbra, tracks, np.zeros(len(tracks), dtype=np.int32), 1)
+        pf = O.Field(dx, dy, 13.7, -4.2)
+        pf.expand(-150.0, 170.0, -140.0, 160.0)
+        pf.freeze()
+        for t in tracks:
+            pf.rasterize(list(t[:, 0]), list(t[:, 1]), umbra)
+        pf.register(1.0)
+        assert (pf.nrows, pf.ncols) == (gm.nrows, gm.ncols)
+        assert np.array_equal(counts, pf.pgrid.astype(np.uint32)), (dx, dy, umbra, step)
