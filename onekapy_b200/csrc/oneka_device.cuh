@@ -860,6 +860,24 @@ __device__ __forceinline__ unsigned long long dkey(double v)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
 
+// ONEKA_RK_LOOP 1 (NOT yet timed on hardware -- prepared for the next round, validated for arithmetic by tests/emu): the six
+// stage evaluations of an attempt as ONE loop instead of six inlined copies.  With the far field on, the unrolled kernel is
+// 4100 SASS instructions (66 KB) and ncu shows instruction-fetch stalls (no_instruction 0.72 per issue) and ~40 spill
+// instructions per attempt; the loop keeps the stage derivatives in local memory by design.
+#ifndef ONEKA_RK_LOOP
+#define ONEKA_RK_LOOP 0
+#endif
+#if ONEKA_RK_LOOP
+// rows 2..7 of the Dormand-Prince tableau (capturezone.py:202-207), six entries each, zero padded
+__constant__ double c_dopri_a[36] = {
+    1.0 / 5.0, 0, 0, 0, 0, 0,
+    3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0,
+    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0,
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0,
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0,
+    35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0};
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
@@ -933,6 +951,36 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
                 ++nattempt;
                 if (fabs(t + dt) > adur) dt = duration - t;                // :223-224
 
+#if ONEKA_RK_LOOP
+                // ONE copy of the velocity evaluation: stages 2..7 in a loop, the stage derivatives in a per-thread array
+                // (local memory, L1-resident), the tableau rows from constant memory.  Same operations in the same order as the
+                // unrolled form below (the zero a71 adds fma(0, k2, .) = identity), so the step sequence is unchanged.
+                double2 kk[7];
+                kk[0] = make_double2(k1x, k1y);
+                double xt = x, yt = y;
+                bool bad = false;
+#pragma unroll 1
+                for (int s = 1; s <= 6; ++s) {
+                    const double *a = c_dopri_a + 6 * (s - 1);
+                    double sx = a[0] * kk[0].x, sy = a[0] * kk[0].y;
+#pragma unroll 1
+                    for (int j = 1; j < s; ++j) {
+                        const double2 kj = kk[j];
+                        sx = fma(a[j], kj.x, sx);
+                        sy = fma(a[j], kj.y, sy);
+                    }
+                    xt = fma(dt, sx, x);
+                    yt = fma(dt, sy, y);
+                    double ox, oy;
+                    const int st = feval(xt, yt, ox, oy);
+                    if (!CONFINED && st) { status = st; running = false; bad = true; break; }
+                    kk[s] = make_double2(ox, oy);
+                }
+                if (bad) break;
+                const double k2x = kk[1].x, k2y = kk[1].y, k3x = kk[2].x, k3y = kk[2].y, k4x = kk[3].x, k4y = kk[3].y;
+                const double k5x = kk[4].x, k5y = kk[4].y, k6x = kk[5].x, k6y = kk[5].y, k7x = kk[6].x, k7y = kk[6].y;
+                (void)k2x; (void)k2y;
+#else
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
                 st = feval(fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
@@ -957,6 +1005,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
                 st = feval(xt, yt, k7x, k7y);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
+#endif
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238
                 const double ey = dt * fma(e5, k6y, fma(e4, k5y, fma(e3, k4y, fma(e2, k3y, fma(e1, k7y, e0 * k1y)))));
                 const double est = fmax(fabs(ex), fabs(ey));

@@ -13,7 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "oneka_emu.cpp")
 DEPS = [SRC, os.path.join(ROOT, "onekapy_b200", "csrc", "oneka_device.cuh"),
         os.path.join(ROOT, "onekapy_b200", "csrc", "oneka_farfield_host.h")]
-OUT = os.path.join(HERE, "_build", "liboneka_emu.so")
+# ONEKA_EMU_DEFINES="-DONEKA_RK_LOOP=1 ..." builds (and tests) the device code with other build knobs
+DEFINES = os.environ.get("ONEKA_EMU_DEFINES", "").split()
+OUT = os.path.join(HERE, "_build", "liboneka_emu%s.so" % ("_" + "_".join(d.lstrip("-D").replace("=", "") for d in DEFINES) if DEFINES else ""))
 _lib = None
 
 
@@ -24,7 +26,7 @@ def build(force=False):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         # -ffp-contract=off: the __d*_rn stand-ins must stay unfused, as the intrinsics are on the device
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I", cuda_inc,
-                               "-I", os.path.join(ROOT, "include"), SRC, "-o", OUT])
+                               "-I", os.path.join(ROOT, "include")] + DEFINES + [SRC, "-o", OUT])
     return OUT
 
 

@@ -73,7 +73,9 @@ def test_no_gpu_fails_loudly(lib):
 
 
 def test_product_never_imports_oracle():
-    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/; the host emulation of the device code
+    (tests/emu) is test infrastructure too and must stay invisible to the package (ONEKA_EMU only appears as the
+    header's own #ifdef)."""
     bad = []
     for top in ("onekapy_b200", "oneka", "include"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
@@ -81,5 +83,7 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     txt = open(os.path.join(dirpath, f)).read()
                     if re.search(r"^\s*(from|import)\s+oracle\b|oneka_oracle|liboneka_oracle", txt, flags=re.M):
+                        bad.append(os.path.join(dirpath, f))
+                    if re.search(r"^\s*(from|import)\s+(tests\.)?emu\b|oneka_emu|define\s+ONEKA_EMU", txt, flags=re.M):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad

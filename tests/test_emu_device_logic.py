@@ -128,3 +128,19 @@ def test_rasteriser_insert_fixture_and_random_tracks(golden):
         pf.register(1.0)
         assert (pf.nrows, pf.ncols) == (gm.nrows, gm.ncols)
         assert np.array_equal(counts, pf.pgrid.astype(np.uint32)), (dx, dy, umbra, step)
+
+
+@pytest.mark.parametrize("defines", ["-DONEKA_RK_LOOP=1 -DONEKA_FF_COEF_GLOBAL=1"])
+def test_prepared_build_knobs_keep_the_arithmetic(defines):
+    """The build knobs that are prepared but not yet timed on hardware (looped Runge-Kutta stages, far-field coefficients read
+    in place) must not change a single step: the whole module again, with the device code built that way."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ONEKA_EMU_DEFINES"):
+        pytest.skip("already running under ONEKA_EMU_DEFINES")
+    env = dict(os.environ, ONEKA_EMU_DEFINES=defines)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_device_logic.py"), "-x", "-q",
+                        "-k", "not prepared_build_knobs"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
