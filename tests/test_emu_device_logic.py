@@ -144,3 +144,24 @@ def test_prepared_build_knobs_keep_the_arithmetic(defines):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_device_logic.py"), "-x", "-q",
                         "-k", "not prepared_build_knobs"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_dry_aquifer_and_attempt_guard(golden):
+    """confined=False forward traces that run dry are truncated at the reference's vertex (PATH_AQUIFER_DRY); the attempt cap
+    ends a path with PATH_MAX_ATTEMPT."""
+    g = golden("unc_dry.npz")
+    base, k, n, H, xo, yo = g["par"]
+    dur, tol, maxstep = g["scal"]
+    spec = FlowSpec(well_xy=g["wells"][:, :2].copy(), xtarget=xo, ytarget=yo, rtarget=0.25, npaths=len(g["starts"]),
+                    duration=dur, base=base, spacing=1.0, umbra=1.0, confined=False, tol=tol, maxstep=maxstep)
+    par = RealizationParams(q=g["wells"][None, :, 3], cond=[k], poro=[n], thick=[H], coef=g["coef"][None, :])
+    out = emu.capture(spec, par, g["starts"], 2, max_verts=512)
+    for p, (t, dry) in enumerate(zip(traces_of(g), g["terminated"])):
+        assert out["status"][0, p] == (1 if dry else 0)
+        assert out["nverts"][0, p] == len(t)
+        assert np.abs(out["verts"][0, p, :len(t)] - t).max() / np.abs(t).max() < 1e-9
+    g = golden("sto_basic.npz")
+    s, spec, par = spec_of(g)
+    spec.max_attempts = 50
+    out = emu.capture(spec, par, start_ring(s["xt"], s["yt"], s["rt"], s["P"]), 2, max_verts=64)
+    assert (out["status"] == 2).all() and (out["attempts"] == 50).all()
