@@ -402,7 +402,10 @@ def run_ours(args):
         cpu = {"value": c["attempts"] / c["seconds"], "unit": "DOPRI5 attempts/s", "cores": c["cores"], "kind": "port",
                "sample": "%d of %d realizations x %d paths, same rows and lattice, OpenMP over realizations, %.1f s"
                          % (c["realizations"], R, P, c["seconds"]),
-               "realizations_per_s": c["realizations"] / c["seconds"]}
+               "realizations_per_s": c["realizations"] / c["seconds"],
+               "python_reference_note": "the reference itself is pure Python and cannot run on this box (it is not in the repo); executed in the "
+                                        "survey container it made 2.5 k attempts/s per core on perham and 5.6 k on basic (BASELINE.md section 2), "
+                                        "~600x slower per core than this C port, which reproduces its traces bit for bit"}
 
     if rank == 0:
         try:

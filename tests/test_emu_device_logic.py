@@ -165,3 +165,31 @@ def test_dry_aquifer_and_attempt_guard(golden):
     spec.max_attempts = 50
     out = emu.capture(spec, par, start_ring(s["xt"], s["yt"], s["rt"], s["P"]), 2, max_verts=64)
     assert (out["status"] == 2).all() and (out["attempts"] == 50).all()
+
+
+@pytest.mark.parametrize("confined", [True, False])
+def test_well_store_remainders_vs_oracle(confined):
+    """0 .. 9 wells: the blocks-of-four well store with its 0-3 leftover wells (both scalings), against the oracle's plain
+    per-well loop; also the far field with so few wells that most tiles have nothing far."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(12)
+    xo, yo = 1000.0, 2000.0
+    for nw in range(0, 10):
+        wxy = np.concatenate([[[xo, yo]], rng.uniform(-900.0, 900.0, (max(nw - 1, 0), 2)) + [xo, yo]])[:nw].reshape(-1, 2)
+        q = np.concatenate([[900.0], rng.uniform(100.0, 600.0, max(nw - 1, 0))])[:nw]
+        coef = np.array([2e-5, -1e-5, 1e-5, -1.3, 0.4, 9000.0])
+        spec = FlowSpec(well_xy=wxy, xtarget=xo, ytarget=yo, rtarget=0.3, npaths=6, duration=400.0, base=0.0, spacing=5.0,
+                        umbra=10.0, confined=confined, tol=1.0, maxstep=15.0)
+        par = RealizationParams(q=q[None, :], cond=[20.0], poro=[0.25], thick=[15.0], coef=coef[None, :])
+        ring = start_ring(xo, yo, 0.3, 6)
+        out = emu.capture(spec, par, ring, 2, max_verts=400)
+        for p in range(6):
+            st, v, na = O.backtrace(wxy, q, 0.0, 20.0, 0.25, 15.0, xo, yo, coef, confined, ring[p, 0], ring[p, 1], 400.0, 1.0, 15.0)
+            assert out["status"][0, p] == st and out["nverts"][0, p] == len(v) and out["attempts"][0, p] == na, (nw, p)
+            assert np.abs(out["verts"][0, p, :len(v)] - v).max() < 1e-7, (nw, p)
+        if confined and nw >= 1:
+            ff = dict(farfield_grid((xo - 600.0, xo + 600.0, yo - 600.0, yo + 600.0), 16), order=28, eta=0.3)
+            far = emu.capture(spec, par, ring, 2, max_verts=400, farfield=ff)
+            assert np.array_equal(far["nverts"], out["nverts"])
+            n = out["nverts"].max()
+            assert np.abs(far["verts"][:, :, :n] - out["verts"][:, :, :n]).max() < 1e-8
