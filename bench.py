@@ -271,7 +271,10 @@ def run_ours(args):
     # ---- set-up (untimed): rows to HBM, lattice from a pilot pass over all realizations ----
     start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, P)
     dp = eng.upload(spec, params, start)
-    eng._farfield_from_pilot(spec, params, dp)      # (large well fields: tile grid from a strided pilot, so that this full pass is fast too)
+    try:                                            # (large well fields: tile grid from a strided pilot, so that this full pass is fast too)
+        eng._farfield_from_pilot(spec, params, dp)
+    except Exception as exc:                        # set-up convenience only: without it the pass below runs on direct sums
+        print("bench: far-field pilot skipped (%r)" % (exc,), file=sys.stderr)
     eng.reset_stats()
     eng.capture(spec, dp)
     bbox = parallel.reduce_bbox(eng.read_stats()["bbox"], group, dev if group is not None else None)
