@@ -37,7 +37,7 @@ def lib():
         vp, d, i, ll = C.c_void_p, C.c_double, C.c_int, C.c_longlong
         _lib.oneka_emu_capture.argtypes = [i, i, vp, d, d, i, d, d, d, ll, ll, i, vp, vp, vp, vp, vp, vp,
                                            d, d, d, d, i, i, d, vp, i, vp, vp, vp, vp, vp,
-                                           i, d, d, d, d, i, i, vp, vp, vp]
+                                           i, d, d, d, d, i, i, vp, vp, vp, vp]
         _lib.oneka_emu_raster_traces.argtypes = [d, d, d, d, i, i, d, ll, vp, vp, vp, ll, vp, vp]
     return _lib
 
@@ -46,9 +46,10 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
-def capture(spec, par, start_xy, mode, geom=None, max_verts=0, farfield=None):
+def capture(spec, par, start_xy, mode, geom=None, max_verts=0, farfield=None, path_bbox=False, clip=None):
     """spec: FlowSpec, par: RealizationParams; mode 0 track / 1 fused (geom needed) / 2 traces.
-    farfield: dict(x0, y0, tile, ntx, nty, order, eta) or None.  -> dict of numpy arrays."""
+    farfield: dict(x0, y0, tile, ntx, nty, order, eta) or None; path_bbox: also return every path's bounding box
+    [R, P, 4]; clip: int32 [R, P, 4] per-path raster windows (mode 1).  -> dict of numpy arrays."""
     wxy = np.ascontiguousarray(spec.well_xy, dtype=np.float64)
     start = np.ascontiguousarray(start_xy, dtype=np.float64)
     R, P = len(par), len(start)
@@ -60,6 +61,10 @@ def capture(spec, par, start_xy, mode, geom=None, max_verts=0, farfield=None):
     counts = np.zeros((geom.nrows, geom.ncols), dtype=np.uint32) if mode == 1 else None
     stats = np.zeros(16, dtype=np.uint64)
     bbox = np.zeros(4)
+    pbb = np.zeros((R, P, 4)) if path_bbox else None
+    if clip is not None:
+        clip = np.ascontiguousarray(clip, dtype=np.int32).reshape(R, P, 4)
+        assert clip.ctypes.data % 16 == 0
     g = geom
     ff = farfield or dict(x0=0.0, y0=0.0, tile=1.0, ntx=1, nty=1, order=0, eta=0.3)
     rc = lib().oneka_emu_capture(
@@ -70,10 +75,10 @@ def capture(spec, par, start_xy, mode, geom=None, max_verts=0, farfield=None):
         g.nrows if g else 0, g.ncols if g else 0, float(spec.umbra), _p(counts),
         int(max_verts), _p(verts), _p(end), _p(nverts), _p(status), _p(attempts),
         int(ff["order"]), float(ff["eta"]), float(ff["x0"]), float(ff["y0"]), float(ff["tile"]), int(ff["ntx"]), int(ff["nty"]),
-        _p(stats), _p(bbox), None)
+        _p(stats), _p(bbox), _p(pbb), _p(clip))
     if rc != 0:
         raise RuntimeError("oneka_emu_capture failed: %d" % rc)
-    return dict(end_xy=end, nverts=nverts, status=status, attempts=attempts, verts=verts, counts=counts,
+    return dict(end_xy=end, nverts=nverts, status=status, attempts=attempts, verts=verts, counts=counts, path_bbox=pbb,
                 stats=dict(attempts=int(stats[0]), steps=int(stats[1]), paths=int(stats[2]), n_not_ok=int(stats[3]),
                            n_clipped=int(stats[4]), exact_tests=int(stats[5]), bbox=tuple(bbox)))
 

@@ -92,7 +92,8 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
                       double xmin, double ymin, double dx, double dy, int nrows, int ncols, double umbra, unsigned int *counts,
                       int max_verts, double *verts, double *end_xy, int *nverts, unsigned char *status, int *attempts,
                       int ff_order, double ff_eta, double ff_x0, double ff_y0, double ff_tile, int ff_ntx, int ff_nty,
-                      unsigned long long *stats_out, double *bbox_out, long long *ff_evals_out)
+                      unsigned long long *stats_out, double *bbox_out, double *path_bbox /*[R][P][4] or null*/,
+                      const int *clip /*[R][P][4] or null (16-byte aligned)*/)
 {
     if (mode < 0 || mode > 2 || R < 0 || P <= 0) return -1;
     TrackParams tp;
@@ -106,6 +107,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
     tp.q = q; tp.cond = cond; tp.poro = poro; tp.thick = thick; tp.coef = coef; tp.start_xy = start_xy;
     tp.end_xy = end_xy; tp.nverts = nverts; tp.status = status; tp.attempts = attempts;
     tp.verts = verts; tp.max_verts = max_verts;
+    tp.path_bbox = path_bbox; tp.clip = clip;
     unsigned long long stats[16];
     std::memset(stats, 0, sizeof(stats));
     stats[STAT_XMIN] = ~0ULL; stats[STAT_YMIN] = ~0ULL;
@@ -181,7 +183,6 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
         bbox_out[0] = undkey(stats[STAT_XMIN]); bbox_out[1] = undkey(stats[STAT_XMAX]);
         bbox_out[2] = undkey(stats[STAT_YMIN]); bbox_out[3] = undkey(stats[STAT_YMAX]);
     }
-    (void)ff_evals_out;
     return 0;
 }
 

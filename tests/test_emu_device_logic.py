@@ -193,3 +193,25 @@ def test_well_store_remainders_vs_oracle(confined):
             assert np.array_equal(far["nverts"], out["nverts"])
             n = out["nverts"].max()
             assert np.abs(far["verts"][:, :, :n] - out["verts"][:, :, :n]).max() < 1e-8
+
+
+@pytest.mark.parametrize("name", ["sto_basic.npz", "sto_perham.npz", "fwd_basic.npz", "det_basic.npz", "unc_basic.npz"])
+def test_exact_clip_pipeline_equals_auto_expanding_reference(golden, name):
+    """Engine.run_exact's pipeline with the device code on the CPU: per-path bounding boxes (tracking pass) -> running
+    union -> per-path clip windows (lattice.clip_windows) -> clipped fused pass == the executed reference's AUTO-EXPANDING
+    grid, cell for cell (probabilityfield.py:298-301, 335)."""
+    import torch
+    from onekapy_b200.lattice import clip_windows
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
+    first = emu.capture(spec, par, ring, 0, path_bbox=True)
+    base = LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"])
+    final = base.expanded(*first["stats"]["bbox"])
+    ref = g["auto_geom"]
+    assert [final.xmin, final.xmax, final.ymin, final.ymax, final.nrows, final.ncols] == list(ref[[0, 1, 2, 3, 6, 7]])
+    clip = clip_windows(torch, base, final, torch.from_numpy(first["path_bbox"])).numpy()
+    out = emu.capture(spec, par, ring, 1, geom=final, clip=clip)
+    want = g["auto_counts"].astype(np.uint32)
+    assert out["counts"].shape == want.shape
+    assert np.count_nonzero(out["counts"] != want) == 0
