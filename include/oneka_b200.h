@@ -181,9 +181,10 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
  * term (3e-15 for eta = 0.3, order = 28); particles outside the grid, unconfined flow and models whose nw / xo / yo
  * differ from the ones given here use the direct sum.  The tables depend on the well COORDINATES only (host pointer;
  * must be the wells later passed as well_xy_dev); the realization-dependent coefficients are formed on the device
- * per launch.  Of the `order` terms the first order_fp64 are evaluated in FP64 and the rest -- whose coefficients are
- * below 2^-24 of the far field once eta^order_fp64 <= 2^-24 -- in FP32 (order_fp64 = 0 chooses that split).
- * nw = 0 or order = 0 switches it off (the default).  Synchronous.
+ * per launch.  order_fp64: only meaningful in builds with ONEKA_FF_TAIL=1, where the first order_fp64 terms are evaluated
+ * in FP64 and the rest -- whose coefficients are below 2^-24 of the far field once eta^order_fp64 <= 2^-24 -- in FP32
+ * (0 chooses that split); the shipped build evaluates every term in FP64 (the FP32 tail measured slower) and
+ * ignores it.  nw = 0 or order = 0 switches the far field off (the default).  Synchronous.
  * max_near_out / mean_near_out (may be NULL): padded length of the longest near list, mean near wells per tile.   */
 int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
                        double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
