@@ -189,6 +189,11 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
 int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
                        double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
                        int32_t order_fp64, int32_t *max_near_out, double *mean_near_out);
+/* Opt-in (default off; arithmetic validated on the host emulation, not yet timed on hardware): also use the far field for
+ * UNCONFINED flow (Model.compute_velocity, oneka/model.py:353-389).  The far wells' part of the potential -- needed only to
+ * decide whether the aquifer is fully saturated at the point -- comes from the same coefficients in FP32; where that decision
+ * is not certain the evaluation falls back to the direct sums with FP64 logs, exactly as without the far field.            */
+int oneka_set_farfield_unconfined(oneka_ctx *ctx, int enabled);
 /* Host restatement of the same tables and evaluation (NO GPU needed; test hook for the expansion's accuracy):
  * out_host[npts][2] = sum_w w_host[w] (x - x_w)/r_w^2, sum_w w_host[w] (y - y_w)/r_w^2 evaluated the far-field way;
  * near_count_out[npts] (may be NULL) = near wells summed directly, or -1 where the point lies outside the grid.   */

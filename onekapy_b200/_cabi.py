@@ -21,7 +21,7 @@ SYMBOLS = [
     "oneka_kernel_ms", "oneka_eval_points_host", "oneka_trace", "oneka_raster_traces", "oneka_capture",
     "oneka_read_stats", "oneka_reset_stats", "oneka_capture_host", "oneka_fp64_probe", "oneka_path_bboxes",
     "oneka_capture_clipped", "oneka_count_histogram", "oneka_gaussian_smooth", "oneka_capture_guarded",
-    "oneka_set_farfield", "oneka_farfield_eval_host",
+    "oneka_set_farfield", "oneka_farfield_eval_host", "oneka_set_farfield_unconfined",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     L.oneka_set_farfield.argtypes = [_vp, C.c_int32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_double)]
+    L.oneka_set_farfield_unconfined.argtypes = [_vp, C.c_int]
     L.oneka_farfield_eval_host.argtypes = [C.c_int32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64, _vp, _vp, _vp]
     for name in SYMBOLS:

@@ -68,6 +68,12 @@ struct oneka_ctx {
         unsigned short *near_cnt = nullptr;   // [ntiles]
         double2 *coef = nullptr;              // [realizations of a launch][ntiles][order], grow-only
         size_t coef_bytes = 0;
+        // unconfined flow (oneka_set_farfield_unconfined)
+        bool unconfined = false;
+        double *Lg = nullptr;                 // [ntiles][nw] ln |z_w - z_c| of the far wells
+        unsigned short *near_idx = nullptr, *near_raw = nullptr;
+        double *b0 = nullptr;                 // [realizations of a launch][ntiles], grow-only
+        size_t b0_bytes = 0;
     } ff;
     // profiling
     bool profiling = false;
@@ -99,7 +105,7 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
     const long long r = blockIdx.x / chunks;
     const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
     FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
-    if (FF) {
+    if (FF && CONFINED) {
 #if ONEKA_FF_COEF_GLOBAL
         const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
         const double2 *s_c64 = ff.coef + (size_t)r * ntiles * order;             // read in place through L1 (all-FP64 builds only)
@@ -128,7 +134,32 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
         }
         fs.c64 = s_c64; fs.c32 = s_c32; fs.off = s_off; fs.cnt = s_cnt;
     }
+    if (FF && !CONFINED) {
+        // unconfined: c64 (discharge) + p32 (potential, p_k = h c_(k-1)/k as float2) + b0 + near well indices
+        const int ntiles = ff.ntx * ff.nty, order = ff.n64;
+        const double h = 0.7071067811865476 / ff.inv_tile;                        // tile / sqrt 2
+        double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
+        float2 *s_p32 = reinterpret_cast<float2 *>(s_c64 + ntiles * order);
+        double *s_b0 = reinterpret_cast<double *>(s_p32 + ntiles * order);
+        unsigned short *s_idx = reinterpret_cast<unsigned short *>(s_b0 + ntiles);
+        unsigned short *s_raw = s_idx + ntiles * ff.max_near;
+        const double2 *g = ff.coef + (size_t)r * ntiles * order;
+        for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) {
+            const int k = i % order;
+            const double2 c = g[i];
+            s_c64[i] = c;
+            const double f = h / (double)(k + 1);
+            s_p32[i] = make_float2((float)(c.x * f), (float)(c.y * f));
+        }
+        for (int i = threadIdx.x; i < ntiles; i += blockDim.x) { s_b0[i] = ff.b0[(size_t)r * ntiles + i]; s_raw[i] = ff.near_raw[i]; }
+        for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_idx[i] = ff.near_idx[i];
+        fs.c64 = s_c64; fs.p32 = s_p32; fs.b0 = s_b0; fs.idx = s_idx; fs.raw = s_raw;
+    }
     stage_realization<CONFINED>(tp, r, rc, s_wells);             // ends with __syncthreads()
+    if (FF && !CONFINED) {                                       // the far potential is one more FP32 sum: <= 3e-6 sum|w| of error,
+        if (threadIdx.x == 0) rc.pot_err *= 1.25;                // far inside a quarter of the screening bound 2e-5 (nw + 16) sum|w|
+        __syncthreads();
+    }
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
     dopri_track<CONFINED, MODE, FF>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
 }
@@ -153,6 +184,33 @@ farfield_coef_kernel(int nw, int ntiles, int order, const double2 *__restrict__ 
             ai = fma(ww, pk.y, ai);
         }
         out[((size_t)r * ntiles + t) * order + k] = make_double2(ar, ai);
+    }
+}
+
+// Unconfined flow: the same coefficients with w_rw = q_rw / (2 pi) (the scaling of stage_realization<false>), plus
+// b0[r][tile] = sum_w w_rw ln|z_w - z_c| over the far wells (thread 0).
+__global__ void __launch_bounds__(32)
+farfield_coef_unc_kernel(int nw, int ntiles, int order, const double2 *__restrict__ P, const double *__restrict__ Lg,
+                         const double *__restrict__ q, double2 *__restrict__ out, double *__restrict__ b0)
+{
+    const long long r = blockIdx.x / ntiles;
+    const int t = (int)(blockIdx.x % ntiles);
+    const double *qr = q + (size_t)r * nw;
+    const double2 *Pt = P + (size_t)t * nw * order;
+    for (int k = threadIdx.x; k < order; k += 32) {
+        double ar = 0.0, ai = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            const double ww = qr[w] * 0.15915494309189535;
+            const double2 pk = Pt[(size_t)w * order + k];
+            ar = fma(ww, pk.x, ar);
+            ai = fma(ww, pk.y, ai);
+        }
+        out[((size_t)r * ntiles + t) * order + k] = make_double2(ar, ai);
+    }
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int w = 0; w < nw; ++w) a = fma(qr[w] * 0.15915494309189535, Lg[(size_t)t * nw + w], a);
+        b0[(size_t)r * ntiles + t] = a;
     }
 }
 
@@ -411,6 +469,12 @@ static size_t ff_smem(const FarFieldDev &ff)
 #endif
 }
 
+static size_t ff_smem_unc(const FarFieldDev &ff)
+{
+    const size_t nt = (size_t)ff.ntx * ff.nty;
+    return (nt * ff.n64 * (sizeof(double2) + sizeof(float2)) + nt * 8 + nt * ff.max_near * 2 + nt * 2 + 15) & ~(size_t)15;
+}
+
 template <int MODE>
 static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps,
                         const FarFieldDev *ff = nullptr)
@@ -420,7 +484,7 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     if (nblk <= 0) return ONEKA_OK;
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
     size_t smem = track_smem(tp.nw);
-    if (ff) smem += ff_smem(*ff);
+    if (ff) smem += m->confined ? ff_smem(*ff) : ff_smem_unc(*ff);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
     prof_begin(ctx, 0);
     FarFieldDev none;
@@ -431,6 +495,9 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     } else if (m->confined) {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         track_kernel<true, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
+    } else if (ff) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<false, MODE, true><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, *ff);
     } else {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         track_kernel<false, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
@@ -447,8 +514,12 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
                             const double *thick, FarFieldDev &out, bool &use)
 {
     const oneka_ctx::FarField &f = ctx->ff;
-    use = f.on && m->confined && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
+    use = f.on && (m->confined || f.unconfined) && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
     if (!use) return ONEKA_OK;
+    if (!m->confined && track_smem(f.nw) + (((size_t)f.ntx * f.nty * f.order * 24 + (size_t)f.ntx * f.nty * (10 + 2 * f.max_near) + 15) & ~(size_t)15) > 200 * 1024) {
+        use = false;                                                  // the unconfined tables (c64 + p32) do not fit: direct sums
+        return ONEKA_OK;
+    }
     const int ntiles = f.ntx * f.nty;
     const size_t need = (size_t)nr * ntiles * f.order * sizeof(double2);
     if (need > ctx->ff.coef_bytes) {
@@ -459,12 +530,25 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     }
     const long long nblk = nr * ntiles;
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many (realization, tile) pairs in one launch (%lld)", nblk);
-    farfield_coef_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, q, poro, thick, ctx->ff.coef);
+    if (m->confined) {
+        farfield_coef_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, q, poro, thick, ctx->ff.coef);
+    } else {
+        const size_t nb0 = (size_t)nr * ntiles * sizeof(double);
+        if (nb0 > ctx->ff.b0_bytes) {
+            if (ctx->ff.b0) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFree(ctx->ff.b0)); ctx->ff.b0 = nullptr; ctx->ff.b0_bytes = 0; }
+            cudaError_t e = cudaMalloc(&ctx->ff.b0, nb0);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(ONEKA_ERR_NOMEM, "cudaMalloc(%zu) for far-field b0 failed: %s", nb0, cudaGetErrorString(e)); }
+            ctx->ff.b0_bytes = nb0;
+        }
+        farfield_coef_unc_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, f.Lg, q, ctx->ff.coef, ctx->ff.b0);
+    }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     out.ntx = f.ntx; out.nty = f.nty; out.n64 = f.n64; out.n32 = f.order - f.n64; out.max_near = f.max_near;
     out.gx0 = f.gx0; out.gy0 = f.gy0; out.inv_tile = 1.0 / f.tile;
     out.coef = ctx->ff.coef; out.near_off = f.near_off; out.near_cnt = f.near_cnt;
+    out.b0 = m->confined ? nullptr : ctx->ff.b0; out.near_idx = f.near_idx; out.near_raw = f.near_raw;
+    if (!m->confined) { out.n64 = f.order; out.n32 = 0; }
     return ONEKA_OK;
 }
 
@@ -574,6 +658,10 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->ff.near_off) cudaFree(ctx->ff.near_off);
     if (ctx->ff.near_cnt) cudaFree(ctx->ff.near_cnt);
     if (ctx->ff.coef) cudaFree(ctx->ff.coef);
+    if (ctx->ff.Lg) cudaFree(ctx->ff.Lg);
+    if (ctx->ff.near_idx) cudaFree(ctx->ff.near_idx);
+    if (ctx->ff.near_raw) cudaFree(ctx->ff.near_raw);
+    if (ctx->ff.b0) cudaFree(ctx->ff.b0);
     delete ctx;
 }
 
@@ -641,6 +729,9 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (f.P) { cudaFree(f.P); f.P = nullptr; }
     if (f.near_off) { cudaFree(f.near_off); f.near_off = nullptr; }
     if (f.near_cnt) { cudaFree(f.near_cnt); f.near_cnt = nullptr; }
+    if (f.Lg) { cudaFree(f.Lg); f.Lg = nullptr; }
+    if (f.near_idx) { cudaFree(f.near_idx); f.near_idx = nullptr; }
+    if (f.near_raw) { cudaFree(f.near_raw); f.near_raw = nullptr; }
     if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
     FFTables T;
     if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
@@ -657,11 +748,24 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     CUDA_TRY(cudaMemcpy(f.P, T.P.data(), T.P.size() * sizeof(double2), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_off, T.off.data(), T.off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_cnt, T.cnt.data(), T.cnt.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&f.Lg, T.Lg.size() * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&f.near_idx, T.idx.size() * sizeof(unsigned short)));
+    CUDA_TRY(cudaMalloc(&f.near_raw, T.cnt_raw.size() * sizeof(unsigned short)));
+    CUDA_TRY(cudaMemcpy(f.Lg, T.Lg.data(), T.Lg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(f.near_idx, T.idx.data(), T.idx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(f.near_raw, T.cnt_raw.data(), T.cnt_raw.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.n64 = n64; f.max_near = T.max_near;
     f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
     f.on = true;
     if (max_near_out) *max_near_out = T.max_near;
     if (mean_near_out) *mean_near_out = T.mean_near;
+    return ONEKA_OK;
+}
+
+int oneka_set_farfield_unconfined(oneka_ctx *ctx, int enabled)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    ctx->ff.unconfined = enabled != 0;
     return ONEKA_OK;
 }
 

@@ -390,8 +390,16 @@ struct FarFieldDev {
     const double2 *coef;             // [R of this launch][ntx*nty][order]  (x = re, y = im)
     const unsigned int *near_off;    // [ntx*nty][max_near]  BYTE offsets of the near wells in the confined well store
     const unsigned short *near_cnt;  // [ntx*nty]            padded (even) list lengths
+    // unconfined flow (appended; null otherwise):
+    const double *b0;                // [R of this launch][ntx*nty]  sum over the far wells of w ln |z_w - z_c|
+    const unsigned short *near_idx;  // [ntx*nty][max_near]  near WELL INDICES (unpadded)
+    const unsigned short *near_raw;  // [ntx*nty]            their counts
 };
-struct FarFieldShared { const double2 *c64; const float2 *c32; const unsigned int *off; const unsigned short *cnt; };
+struct FarFieldShared {
+    const double2 *c64; const float2 *c32; const unsigned int *off; const unsigned short *cnt;
+    // unconfined flow: the potential's polynomial p_k = h c_(k-1)/k (k = 1..order) as float2, b0 per tile, near well indices
+    const float2 *p32; const double *b0; const unsigned short *idx; const unsigned short *raw;
+};
 // shared-memory layout of a tracking CTA:
 //   [well store + 256 B of slack][c64 ntiles x n64 double2][c32 ntiles x n32 float2][near_off][near_cnt];
 // the dummy well {b = 1e100, c = (1, 1)} that pads odd near lists sits in the slack right behind the confined store
@@ -578,6 +586,68 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     fx = (gx + hx) + re;
     fy = (gy + hy) - im;
     return PATH_OK;
+}
+
+// ---- unconfined flow through the far field (opt-in: oneka_set_farfield_unconfined; timed next round) ---------------------------
+// field_feval<false> needs, besides the discharge, the POTENTIAL -- but only to decide whether the aquifer is fully saturated at
+// the point (then V = Q/(H n) whatever Phi is), which an FP32-accurate value settles almost everywhere.  The far wells' part of it,
+//     sum_far w ln|z - z_w| = b0 + Re sum_{k>=1} p_k zeta^k,     b0 = sum_far w ln|z_w - z_c|,   p_k = h c_(k-1) / k,
+// comes from the SAME coefficients as the discharge (d/dz of the complex potential), so it costs one more Horner, in FP32.  Where
+// the screening value is within pot_err of k H^2/2 (or the point lies outside the tile grid) the whole evaluation is redone by the
+// direct-sum function, FP64 logs and all -- exactly what field_feval<false> does there.
+__device__ __noinline__ int field_direct_unc_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
+{
+    return field_feval<false>(rc, s_wells, nw, x, y, fx, fy);
+}
+
+__device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
+                                                  const FarFieldDev &ff, const FarFieldShared &fs,
+                                                  double x, double y, double &fx, double &fy)
+{
+    const double dx0 = x - rc.xo;
+    const double dy0 = y - rc.yo;
+    int tile;
+    double zr, zi;
+    if (!ff_locate(ff.ntx, ff.nty, ff.gx0, ff.gy0, ff.inv_tile, dx0, dy0, tile, zr, zi))
+        return field_direct_unc_cold(rc, s_wells, nw, x, y, fx, fy);
+    double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
+    double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
+    // near wells: discharge term + FP32 log term each (well_term, the unconfined store)
+    float lsum32 = 0.0f;
+    const unsigned short *pi = fs.idx + tile * ff.max_near;
+    const int n = fs.raw[tile];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const int w = pi[i];
+        well_term(x, y, well_x(s_wells, w), well_y(s_wells, w), well_w(s_wells, w),
+                  reinterpret_cast<const float *>(s_wells + (w >> 2) * WELL_BLK + 12)[w & 3], gx, gy, lsum32);
+    }
+    // far wells: discharge polynomial in FP64 ...
+    const int order = ff.n64;
+    double re, im;
+    ff_poly_eval<false>(fs.c64 + tile * order, order, zr, zi, 0.0, 0.0, re, im);
+    gx += re;
+    gy -= im;
+    // ... and their potential in FP32:  Re(zeta T),  T = sum_j p_(j+1) zeta^j
+    const float2 *pp = fs.p32 + tile * order;
+    const float fr = (float)zr, fi = (float)zi;
+    float ar = 0.0f, ai = 0.0f;
+#pragma unroll 2
+    for (int j = order - 1; j >= 0; --j) {
+        const float2 c = pp[j];
+        const float nr = fmaf(ar, fr, fmaf(-ai, fi, c.x));
+        const float ni = fmaf(ar, fi, fmaf(ai, fr, c.y));
+        ar = nr; ai = ni;
+    }
+    const double pot_far = fs.b0[tile] + (double)fmaf(fr, ar, -(fi * ai));
+    const double pot_reg = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
+    const double pot_apx = fma(0.34657359027997264, (double)lsum32, pot_reg) + pot_far;
+    if (pot_apx - rc.pot_err > rc.half_kH2) {                    // certainly saturated: model.py:382-384
+        fx = gx * rc.inv_Hn;
+        fy = gy * rc.inv_Hn;
+        return PATH_OK;
+    }
+    return field_direct_unc_cold(rc, s_wells, nw, x, y, fx, fy);
 }
 #endif
 
@@ -889,7 +959,8 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 {
     // the velocity: direct sum over the wells, or (FF, confined only) near wells + the tile's far-field polynomial
     auto feval = [&](double px, double py, double &ox, double &oy) -> int {
-        if constexpr (FF) return field_feval_ff(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
+        if constexpr (FF && CONFINED) return field_feval_ff(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
+        else if constexpr (FF) return field_feval_ff_unc(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
         else return field_feval<CONFINED>(rc, s_wells, tp.nw, px, py, ox, oy);
     };
     // Dormand-Prince tableau, capturezone.py:202-209

@@ -17,6 +17,9 @@ struct FFTables {
     std::vector<unsigned int> off;             // [ntiles][max_near] byte offsets into the well store (padded with the dummy well)
     std::vector<unsigned short> cnt;           // [ntiles] padded (even) lengths
     std::vector<int> near_flat, near_begin;    // unpadded near lists (host evaluator)
+    // unconfined flow only (the potential's far part, see field_feval_ff_unc):
+    std::vector<double> Lg;                    // [ntiles][nw] ln |z_w - z_c| for far wells, 0 for near wells
+    std::vector<unsigned short> idx, cnt_raw;  // [ntiles][max_near] near WELL INDICES (unpadded lists), [ntiles] their lengths
 };
 
 // terms kept in FP64: the smallest even k with eta^k <= 2^-24 (see ff_tail_eval), at most `order`
@@ -48,6 +51,7 @@ static inline const char *build_ff_tables(int nw, const double *well_xy, double 
     const long double rfar = h / (long double)eta;
     T.ntiles = ntiles;
     T.P.assign((size_t)ntiles * nw * order, make_double2(0.0, 0.0));
+    T.Lg.assign((size_t)ntiles * nw, 0.0);
     T.near_flat.clear();
     T.near_begin.assign(ntiles + 1, 0);
     int maxn = 0;
@@ -60,6 +64,7 @@ static inline const char *build_ff_tables(int nw, const double *well_xy, double 
                 const long double dx = ((long double)well_xy[2 * w] - xo) - cx, dy = ((long double)well_xy[2 * w + 1] - yo) - cy;
                 const long double d2 = dx * dx + dy * dy;
                 if (!(sqrtl(d2) >= rfar)) { T.near_flat.push_back(w); continue; }          // near (or nan): summed directly
+                T.Lg[(size_t)t * nw + w] = (double)(0.5L * logl(d2));
                 const long double ir = dx / d2, ii = -dy / d2;                              // 1/(z_w - z_c)
                 const long double ur = h * ir, ui = h * ii;                                 // h/(z_w - z_c)
                 long double tr = -ir, tim = -ii;                                            // term_0 = -1/(z_w - z_c)
@@ -81,6 +86,9 @@ static inline const char *build_ff_tables(int nw, const double *well_xy, double 
     const unsigned int dummy = (unsigned int)ff_dummy_offset(nw) * 8u;
     T.off.assign((size_t)ntiles * T.max_near, dummy);
     T.cnt.assign(ntiles, 0);
+    T.cnt_raw.assign(ntiles, 0);
+    T.idx.assign((size_t)ntiles * T.max_near, 0);
+    if (nw > 65535) return "far field: too many wells for 16-bit near lists";
     for (int t = 0; t < ntiles; ++t) {
         const int n = T.near_begin[t + 1] - T.near_begin[t];
         for (int i = 0; i < n; ++i) {
@@ -88,6 +96,8 @@ static inline const char *build_ff_tables(int nw, const double *well_xy, double 
             T.off[(size_t)t * T.max_near + i] = (unsigned int)((w >> 2) * SWELL_BLK + 3 * (w & 3)) * 8u;
         }
         T.cnt[t] = (unsigned short)((n + 1) & ~1);
+        T.cnt_raw[t] = (unsigned short)n;
+        for (int i = 0; i < n; ++i) T.idx[(size_t)t * T.max_near + i] = (unsigned short)T.near_flat[T.near_begin[t] + i];
     }
     return nullptr;
 }
@@ -106,6 +116,17 @@ static inline void ff_host_coefficients(const FFTables &T, int nw, int order, co
             }
             coef[(size_t)t * order + k] = make_double2(ar, ai);
         }
+}
+
+// unconfined flow: c[tile][k] with w = q/(2 pi) and b0[tile] = sum_far w ln |z_w - z_c|, as farfield_coef_unc_kernel forms them
+static inline void ff_host_b0(const FFTables &T, int nw, const double *w, std::vector<double> &b0)
+{
+    b0.assign(T.ntiles, 0.0);
+    for (int t = 0; t < T.ntiles; ++t) {
+        double a = 0.0;
+        for (int j = 0; j < nw; ++j) a = fma(w[j], T.Lg[(size_t)t * nw + j], a);
+        b0[t] = a;
+    }
 }
 
 }  // namespace oneka

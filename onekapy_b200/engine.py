@@ -158,6 +158,10 @@ class Engine:
         self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "64"))
         self.farfield_order_fp64 = int(os.environ.get("ONEKA_FARFIELD_FP64", "0"))      # 0 = automatic FP64 / FP32 split
         self.farfield_min_wells = 12
+        # opt-in, not yet timed on hardware: the far field for confined=False too (oneka_set_farfield_unconfined)
+        self._ff_unconfined = False
+        if os.environ.get("ONEKA_FARFIELD_UNCONFINED", "0").lower() in ("1", "on", "yes"):
+            self.farfield_unconfined = True
         self._ff_key = None
         self._ff_info = None
         self.use_stream(torch.cuda.current_stream(self.device))
@@ -235,6 +239,15 @@ class Engine:
         return (len(spec.well_xy), float(spec.xtarget), float(spec.ytarget),
                 np.ascontiguousarray(spec.well_xy, dtype=np.float64).tobytes())
 
+    @property
+    def farfield_unconfined(self):
+        return self._ff_unconfined
+
+    @farfield_unconfined.setter
+    def farfield_unconfined(self, on):
+        self._ff_unconfined = bool(on)
+        _cabi.check(self._L.oneka_set_farfield_unconfined(self._h, int(self._ff_unconfined)))
+
     def _auto_farfield(self, spec: FlowSpec, geom: Optional[LatticeGeom], box=None):
         """Called before every capture: keep / build / drop the far-field tables for this spec and lattice.
         Tracking-only calls (geom None) keep tables built for the same wells (a particle outside the tile grid takes
@@ -242,7 +255,7 @@ class Engine:
         expected, when that is known to be tighter than the lattice (Engine.run's work lattice carries a 25 % safety
         margin per side; tiles sized for it would be 1.5x larger and their near lists twice as long)."""
         nw = len(spec.well_xy)
-        if self.farfield == "off" or not spec.confined or nw < self.farfield_min_wells:
+        if self.farfield == "off" or not (spec.confined or self._ff_unconfined) or nw < self.farfield_min_wells:
             if self._ff_key is not None:
                 self.set_farfield(None)
             return
@@ -271,7 +284,7 @@ class Engine:
         (direct sums, <= pilot x pilot_paths particles) estimates the extents and the tables are built on them.  A
         particle that leaves the estimate takes the direct sum, so a poor estimate only costs time."""
         R = len(params)
-        if (self.farfield == "off" or not spec.confined or len(spec.well_xy) < self.farfield_min_wells or R == 0
+        if (self.farfield == "off" or not (spec.confined or self._ff_unconfined) or len(spec.well_xy) < self.farfield_min_wells or R == 0
                 or (self._ff_key is not None and self._ff_key[0] == self._ff_wells_key(spec))):
             return
         start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)

@@ -119,7 +119,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
     double s_lat[5] = {L.xmin, L.ymin, L.dx, L.dy, L.umbra2};
 
     // far-field tables (geometry) once; coefficients per realization
-    const bool use_ff = ff_order > 0 && confined;
+    const bool use_ff = ff_order > 0;                          // unconfined: the opt-in path of oneka_set_farfield_unconfined
     FFTables T;
     FarFieldDev ff;
     std::memset(&ff, 0, sizeof(ff));
@@ -133,12 +133,27 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
     std::vector<unsigned int> bitmap(mode == 1 ? (size_t)L.words : 1, 0u);
     std::vector<double> wsc(nw > 0 ? nw : 1);
     std::vector<double2> c64;
+    std::vector<float2> p32;
+    std::vector<double> b0;
     RealConsts rc;
     for (long long r = 0; r < R; ++r) {
         if (confined) stage_realization<true>(tp, r, rc, s_wells.data());
         else stage_realization<false>(tp, r, rc, s_wells.data());
         FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
-        if (use_ff) {
+        if (use_ff && !confined) {                                                                       // track_kernel<false, ., true>'s staging
+            for (int w = 0; w < nw; ++w) wsc[w] = q[(size_t)r * nw + w] * 0.15915494309189535;           // farfield_coef_unc_kernel
+            ff_host_coefficients(T, nw, ff_order, wsc.data(), c64);
+            ff_host_b0(T, nw, wsc.data(), b0);
+            const double h = 0.7071067811865476 / ff.inv_tile;
+            p32.resize(c64.size());
+            for (size_t i = 0; i < c64.size(); ++i) {
+                const double f = h / (double)(i % ff_order + 1);
+                p32[i] = make_float2((float)(c64[i].x * f), (float)(c64[i].y * f));
+            }
+            fs.c64 = c64.data(); fs.p32 = p32.data(); fs.b0 = b0.data(); fs.idx = T.idx.data(); fs.raw = T.cnt_raw.data();
+            rc.pot_err *= 1.25;
+        }
+        if (use_ff && confined) {
             const double scale = 1.0 / (thick[r] * poro[r]);
             for (int w = 0; w < nw; ++w) wsc[w] = q[(size_t)r * nw + w] * 0.15915494309189535 * scale;   // farfield_coef_kernel
             ff_host_coefficients(T, nw, ff_order, wsc.data(), c64);
@@ -157,6 +172,10 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
                     else if (mode == 1) dopri_track<true, 1, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true);
                     else dopri_track<true, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 }
+            } else if (use_ff) {
+                if (mode == 0) dopri_track<false, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
+                else if (mode == 1) dopri_track<false, 1, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
+                else dopri_track<false, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
             } else {
                 if (mode == 0) dopri_track<false, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 else if (mode == 1) dopri_track<false, 1, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true);

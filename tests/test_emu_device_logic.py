@@ -215,3 +215,30 @@ def test_exact_clip_pipeline_equals_auto_expanding_reference(golden, name):
     want = g["auto_counts"].astype(np.uint32)
     assert out["counts"].shape == want.shape
     assert np.count_nonzero(out["counts"] != want) == 0
+
+
+def test_unconfined_far_field_vs_direct_and_oracle():
+    """field_feval_ff_unc (opt-in, oneka_set_farfield_unconfined): the perham and 200-well fields with confined=False --
+    thick aquifers (saturated nowhere near the wells: the FP64 fallback runs) and thin ones (saturated everywhere: the FP32
+    screening decides) -- keep every step of the direct-sum kernel, and the oracle's."""
+    import bench
+    from oracle import oracle as O
+    for name, R, P, thick_scale in [("c3", 3, 12, 1.0), ("c3", 2, 12, 40.0), ("c4", 2, 10, 1.0), ("c4", 1, 10, 8.0)]:
+        spec, par, _ = bench.make_workload(name, R, P, 3, unconfined=True)
+        par = RealizationParams(q=par.q, cond=par.cond, poro=par.poro, thick=par.thick * thick_scale, coef=par.coef)
+        ring = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, P)
+        direct = emu.capture(spec, par, ring, 2, max_verts=1500)
+        bb = direct["stats"]["bbox"]
+        ff = dict(farfield_grid((bb[0] - 20, bb[1] + 20, bb[2] - 20, bb[3] + 20), 64), order=28, eta=0.3)
+        far = emu.capture(spec, par, ring, 2, max_verts=1500, farfield=ff)
+        assert np.array_equal(far["status"], direct["status"]) and np.array_equal(far["nverts"], direct["nverts"])
+        assert np.array_equal(far["attempts"], direct["attempts"])
+        n = direct["nverts"].max()
+        scale = np.maximum(np.abs(direct["verts"][:, :, :n]).max(axis=3), 1.0)
+        assert (np.abs(far["verts"][:, :, :n] - direct["verts"][:, :, :n]).max(axis=3) / scale).max() < 1e-11
+        for r in range(R):
+            for p in (0, P // 2):
+                st, v, na = O.backtrace(spec.well_xy, par.q[r], spec.base, par.cond[r], par.poro[r], par.thick[r], spec.xtarget,
+                                        spec.ytarget, par.coef[r], False, ring[p, 0], ring[p, 1], spec.duration, spec.tol, spec.maxstep)
+                assert far["status"][r, p] == st and far["nverts"][r, p] == len(v) and far["attempts"][r, p] == na
+                assert np.abs(far["verts"][r, p, :len(v)] - v).max() / np.abs(v).max() < 1e-9

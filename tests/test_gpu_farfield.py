@@ -134,3 +134,31 @@ def test_farfield_off_for_small_fields_and_unconfined(eng, golden):
     gm = fixed_geom(g, s)
     eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
     assert eng.farfield_info() is None
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ONEKA_TEST_UNCONFINED_FF", "0") != "1",
+                    reason="opt-in path (Engine.farfield_unconfined) validated on the host emulation only so far; "
+                           "set ONEKA_TEST_UNCONFINED_FF=1 to run it on the device")
+def test_unconfined_farfield_vs_direct(eng):
+    import bench
+    from onekapy_b200.engine import RealizationParams
+    for name, thick_scale in [("c3", 1.0), ("c4", 1.0), ("c4", 8.0)]:
+        spec, par, _ = bench.make_workload(name, 4, 64, 3, unconfined=True)
+        par = RealizationParams(q=par.q, cond=par.cond, poro=par.poro, thick=par.thick * thick_scale, coef=par.coef)
+        dp = eng.upload(spec, par)
+        eng.farfield_unconfined = False
+        geom, _ = lattice_for(eng, spec, dp)
+        a = eng.new_counts(geom)
+        eng.reset_stats()
+        eng.capture(spec, dp, geom, a)
+        sa = eng.read_stats()
+        assert eng.farfield_info() is None
+        eng.farfield_unconfined = True
+        b = eng.new_counts(geom)
+        eng.reset_stats()
+        eng.capture(spec, dp, geom, b)
+        sb = eng.read_stats()
+        assert eng.farfield_info() is not None
+        assert sa["attempts"] == sb["attempts"] and sa["steps"] == sb["steps"] and sa["n_not_ok"] == sb["n_not_ok"]
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+        eng.farfield_unconfined = False
