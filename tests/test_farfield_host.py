@@ -120,3 +120,72 @@ def test_farfield_grid_covers_the_box():
         assert 1 <= g["ntx"] * g["nty"] <= max_tiles and g["tile"] >= 100.0
         assert g["x0"] <= box[0] and g["x0"] + g["ntx"] * g["tile"] >= box[1]
         assert g["y0"] <= box[2] and g["y0"] + g["nty"] * g["tile"] >= box[3]
+
+
+class _FakeLib:
+    """Records the far-field calls Engine makes; answers with a mean near count."""
+    def __init__(self, mean_near):
+        self.calls, self.mean_near = [], mean_near
+
+    def oneka_set_farfield(self, h, nw, wxy, xo, yo, x0, y0, tile, ntx, nty, order, eta, fp64, mx, mean):
+        self.calls.append(("set", int(nw), int(order)))
+        if nw and mean is not None:
+            mx._obj.value, mean._obj.value = 4, self.mean_near
+        return 0
+
+    def oneka_set_farfield_unconfined(self, h, on):
+        self.calls.append(("unconfined", int(on)))
+        return 0
+
+
+def _stub_engine(mean_near):
+    from onekapy_b200.engine import Engine
+    e = object.__new__(Engine)
+    e._L, e._h = _FakeLib(mean_near), None
+    e.farfield, e.farfield_order, e.farfield_eta, e.farfield_max_tiles = "auto", 28, 0.3, 64
+    e.farfield_order_fp64, e.farfield_min_wells, e._ff_unconfined = 0, 12, False
+    e._ff_key = e._ff_info = None
+    return e
+
+
+def test_engine_far_field_policy_without_a_gpu():
+    """Engine._auto_farfield: when the tables are built, kept, rebuilt and dropped (the C ABI replaced by a recorder)."""
+    from onekapy_b200.engine import FlowSpec
+    from onekapy_b200.lattice import LatticeGeom
+    wxy, w, xo, yo = _field("perham")
+    spec = FlowSpec(well_xy=wxy, xtarget=xo, ytarget=yo, rtarget=0.2, npaths=10, duration=100.0, base=0.0, spacing=4.0,
+                    umbra=8.0, confined=True, tol=1.0, maxstep=10.0)
+    geom = LatticeGeom.anchored(4.0, 4.0, xo, yo).expanded(xo - 900.0, xo + 900.0, yo - 700.0, yo + 700.0)
+    e = _stub_engine(2.0)
+    e._auto_farfield(spec, None)                                   # tracking only, nothing configured: stays direct
+    assert e._L.calls == [] and e.farfield_info() is None
+    e._auto_farfield(spec, geom)                                   # 29 wells, 2 near: worth it
+    assert e._L.calls == [("set", 29, 28)] and e.farfield_info()["mean_near"] == 2.0
+    e._auto_farfield(spec, geom)                                   # same lattice: kept, no call
+    e._auto_farfield(spec, None)                                   # tracking-only pass of the same wells: kept
+    assert len(e._L.calls) == 1
+    e._auto_farfield(spec, geom, box=(xo - 500.0, xo + 500.0, yo - 400.0, yo + 400.0))    # tighter box: rebuilt
+    assert len(e._L.calls) == 2 and e.farfield_info()["tile"] < 200.0
+    other = FlowSpec(**{**spec.__dict__, "well_xy": wxy + 1.0})
+    e._auto_farfield(other, None)                                  # other wells, no lattice: tables dropped
+    assert e._L.calls[-1] == ("set", 0, 0) and e.farfield_info() is None
+    spec.confined = False
+    e._auto_farfield(spec, geom)                                   # unconfined: direct unless opted in
+    assert e.farfield_info() is None and e._L.calls[-1] == ("set", 0, 0)
+    e.farfield_unconfined = True
+    e._auto_farfield(spec, geom)
+    assert e._L.calls[-2:] == [("unconfined", 1), ("set", 29, 28)] and e.farfield_info() is not None
+    # too many near wells (cost model): tables built, measured, dropped -- and the decision remembered
+    e2 = _stub_engine(25.0)
+    spec.confined = True
+    e2._auto_farfield(spec, geom)
+    assert e2._L.calls == [("set", 29, 28), ("set", 0, 0)] and e2.farfield_info() is None
+    e2._auto_farfield(spec, geom)
+    assert len(e2._L.calls) == 2
+    # few wells / switched off: never
+    e3 = _stub_engine(0.0)
+    small = FlowSpec(**{**spec.__dict__, "well_xy": wxy[:5].copy()})
+    e3._auto_farfield(small, geom)
+    e3.farfield = "off"
+    e3._auto_farfield(spec, geom)
+    assert e3._L.calls == []
