@@ -20,6 +20,8 @@ recorded inputs are stored, as small .npz files:
   sto_perham.npz     same for data/perham.py, 2 x 20
   unc_basic.npz      confined=False path, 3 x 8 (+ a trace that raises AquiferError)
   fwd_basic.npz      negative duration (forward tracking) from injection wells (data/basic.py, discharges negated)
+  sto_wells200.npz   the stochastic path on this repo's synthetic 200-well field (onekapy_b200/synthetic.py), 1 x 10: the
+                     executed reference on a field large enough for the far-field compression to carry most of the wells
 
 Sampling follows `oneka/stochastic.py:220-241` line by line, except that the A-F draw
 uses ONE seeded Generator instead of a fresh unseeded one per realization (`:241`),
@@ -293,8 +295,20 @@ def injection_variant(modname):
     return m
 
 
+def synthetic_module(nwells):
+    """onekapy_b200.synthetic.well_field as an object with the attributes of a reference data module."""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from onekapy_b200 import synthetic
+    pb = synthetic.well_field(nwells)
+    return types.SimpleNamespace(**{k.upper(): v for k, v in pb.items()})
+
+
 def gen_capture(name, modname, nreal, npaths, seed, confined=None, deterministic=False, duration=None, injection=False):
-    m = injection_variant(modname) if injection else importlib.import_module("data." + modname)
+    if not isinstance(modname, str):
+        m = modname
+    else:
+        m = injection_variant(modname) if injection else importlib.import_module("data." + modname)
     confined = m.CONFINED if confined is None else confined
     if deterministic:
         # oneka/deterministic.py:185-199
@@ -372,7 +386,7 @@ def gen_unconfined_dry():
 if __name__ == "__main__":
     import logging
     logging.disable(logging.CRITICAL)
-    which = sys.argv[1:] or ["points", "fit", "distsq", "expand", "insert", "det", "sto", "perham", "unc", "fwd", "dry"]
+    which = sys.argv[1:] or ["points", "fit", "distsq", "expand", "insert", "det", "sto", "perham", "unc", "fwd", "dry", "wells200"]
     if "points" in which:
         gen_model_points()
     if "fit" in which:
@@ -395,3 +409,5 @@ if __name__ == "__main__":
         gen_capture("fwd_basic.npz", "basic", 2, 6, seed=21, duration=-1500.0, injection=True)
     if "dry" in which:
         gen_unconfined_dry()
+    if "wells200" in which:
+        gen_capture("sto_wells200.npz", synthetic_module(200), 1, 10, seed=31)

@@ -11,7 +11,7 @@ from emu import emu
 from onekapy_b200.engine import FlowSpec, RealizationParams, start_ring, farfield_grid
 from onekapy_b200.lattice import LatticeGeom
 
-CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz"]
+CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz", "sto_wells200.npz"]
 
 
 def spec_of(g):
@@ -80,6 +80,24 @@ def test_far_field_evaluation_in_the_tracker(golden, tiles, shrink):
     n = far["nverts"].max()
     scale = np.maximum(np.abs(direct["verts"][:, :, :n]).max(axis=3), 1.0)
     assert (np.abs(far["verts"][:, :, :n] - direct["verts"][:, :, :n]).max(axis=3) / scale).max() < 1e-12
+    fused = emu.capture(spec, par, ring, 1, geom=gm, farfield=ff)
+    assert np.array_equal(fused["counts"], g["fixed_counts"].astype(np.uint32))
+
+
+def test_far_field_200_wells_vs_executed_reference(golden):
+    """The synthetic 200-well field, traced by the EXECUTED reference (tests/golden/sto_wells200.npz): with the far field
+    carrying ~195 of the 200 wells the tracker still reproduces every vertex and the fused pass every cell."""
+    g = golden("sto_wells200.npz")
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
+    ff = ff_box(g, spec, 64)
+    out = emu.capture(spec, par, ring, 2, max_verts=1024, farfield=ff)
+    worst = 0.0
+    for p, t in enumerate(traces_of(g)):
+        assert out["nverts"][0, p] == len(t)
+        worst = max(worst, (np.abs(out["verts"][0, p, :len(t)] - t).max(axis=1) / np.abs(t).max(axis=1)).max())
+    assert worst < 1e-12, worst
     fused = emu.capture(spec, par, ring, 1, geom=gm, farfield=ff)
     assert np.array_equal(fused["counts"], g["fixed_counts"].astype(np.uint32))
 
@@ -195,7 +213,7 @@ def test_well_store_remainders_vs_oracle(confined):
             assert np.abs(far["verts"][:, :, :n] - out["verts"][:, :, :n]).max() < 1e-8
 
 
-@pytest.mark.parametrize("name", ["sto_basic.npz", "sto_perham.npz", "fwd_basic.npz", "det_basic.npz", "unc_basic.npz"])
+@pytest.mark.parametrize("name", ["sto_basic.npz", "sto_perham.npz", "fwd_basic.npz", "det_basic.npz", "unc_basic.npz", "sto_wells200.npz"])
 def test_exact_clip_pipeline_equals_auto_expanding_reference(golden, name):
     """Engine.run_exact's pipeline with the device code on the CPU: per-path bounding boxes (tracking pass) -> running
     union -> per-path clip windows (lattice.clip_windows) -> clipped fused pass == the executed reference's AUTO-EXPANDING

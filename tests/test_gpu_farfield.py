@@ -83,6 +83,31 @@ def test_fused_capture_with_farfield_bit_exact(eng, golden):
     assert st2["attempts"] == st["attempts"] and np.array_equal(c2.cpu().numpy(), counts.cpu().numpy())
 
 
+def test_200_wells_vs_executed_reference(eng, golden):
+    """tests/golden/sto_wells200.npz: the synthetic 200-well field traced by the executed reference."""
+    g = golden("sto_wells200.npz")
+    s, spec, par = spec_of(g)
+    gm = fixed_geom(g, s)
+    dp = eng.upload(spec, par)
+    counts = eng.new_counts(gm)
+    eng.reset_stats()
+    pp = eng.capture(spec, dp, gm, counts, per_path=True)
+    st = eng.read_stats()
+    info = eng.farfield_info()
+    assert info is not None and info["mean_near"] < 20
+    tr = traces_of(g)
+    assert np.array_equal(pp["nverts"].cpu().numpy().ravel(), [len(t) for t in tr])
+    assert st["steps"] == sum(len(t) - 1 for t in tr) and st["n_not_ok"] == 0
+    end_ref = np.array([t[-1] for t in tr]).reshape(1, s["P"], 2)
+    rel = (np.abs(pp["end_xy"].cpu().numpy() - end_ref).max(axis=2) / np.abs(end_ref).max(axis=2)).max()
+    assert rel < POS_RTOL
+    assert np.array_equal(counts.cpu().numpy().view(np.uint32), g["fixed_counts"].astype(np.uint32))
+    out = eng.trace(spec, dp, max_verts=512)
+    worst = max((np.abs(out["verts"][0, p, :len(t)] - t).max(axis=1) / np.abs(t).max(axis=1)).max() for p, t in enumerate(tr))
+    print("200 wells (mean near %.1f): max rel vertex error vs the executed reference %.3e" % (info["mean_near"], worst))
+    assert worst < POS_RTOL
+
+
 def test_particles_outside_the_tile_grid_take_the_direct_sum(eng, golden):
     """Tile grid over the lower-left quarter of the traces only: three quarters of the evaluations fall back."""
     g = golden("sto_perham.npz")

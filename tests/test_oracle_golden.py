@@ -14,7 +14,7 @@ import pytest
 from oracle import oracle as O
 from helpers import scal, geom, traces_of
 
-CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz"]
+CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz", "fwd_basic.npz", "sto_wells200.npz"]
 
 
 # ---- reference tests/test_model.py:26-42 fixture ---------------------------------------
