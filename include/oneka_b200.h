@@ -41,6 +41,7 @@ extern "C" {
 #define ONEKA_ERR_CUDA     -2
 #define ONEKA_ERR_NOMEM    -3
 #define ONEKA_ERR_NODEVICE -4
+#define ONEKA_ERR_NCCL     -5
 
 /* per-path status words (status[R][P]) */
 #define ONEKA_PATH_OK          0
@@ -153,6 +154,19 @@ int oneka_capture_guarded(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
                           uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
                           uint32_t *clipped_dev);
 
+/* ---- Guarded capture that also reports every path's bounding box ----------------------------- *
+ * oneka_capture_guarded plus bbox_dev[R][P][4] = min x, max x, min y, max y of each path's vertices (either of
+ * clipped_dev / bbox_dev may be NULL).  One fused pass then serves BOTH the count grid and the running union of
+ * bounding boxes from which the reference's order-dependent clip (next section) is decided: only the realizations
+ * containing a path whose windows the reference's grid-at-that-moment would have clipped are re-rasterised with
+ * oneka_capture_clipped (Engine.run_exact) -- instead of a full tracking pass before the fused one.               */
+int oneka_capture_tracked(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
+                          uint32_t *clipped_dev, double *bbox_dev);
+
 /* ---- Exact emulation of the reference's auto-expanding field ----------------------------- *
  * The reference expands its grid to each trace's bounding box just before inserting it
  * (ProbabilityField.rasterize, oneka/probabilityfield.py:335) and insert() clips every segment's
@@ -228,6 +242,41 @@ int oneka_capture_host(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_la
 int oneka_count_histogram(oneka_ctx *ctx, const uint32_t *counts_dev, int64_t ncell, int32_t nbins, uint64_t *hist_dev);
 int oneka_gaussian_smooth(oneka_ctx *ctx, const uint32_t *counts_dev, int32_t nrows, int32_t ncols, double total_weight,
                           const double *w_host, int32_t lw, double *tmp_dev, double *out_dev);
+
+/* ---- The one collective of the path: sum of the per-GPU count grids ------------------------- *
+ * Realizations shard over GPUs with no exchange until the end; the only shared state of the reference's loop is the
+ * additive grid (ProbabilityField.register, oneka/probabilityfield.py:357-358: pgrid[rgrid] += weight, total_weight += weight).
+ * oneka_allreduce_counts is that sum: ncclAllReduce(counts, uint32, sum), in place, enqueued on the context's stream
+ * (so it orders after the captures that filled `counts` without a host synchronisation).  Integer sums are
+ * order-independent: the reduced grid is bit-identical for any number of GPUs.
+ *   oneka_comm_unique_id   fills 128 bytes (ncclUniqueId) on ONE rank; the caller ships them to the others by any means
+ *                          (torch.distributed broadcast, MPI, a file ...);
+ *   oneka_comm_init_rank   joins the communicator (collective over all nranks contexts; the context owns it);
+ *   oneka_comm_attach      alternatively borrow an existing ncclComm_t (e.g. the host framework's); not destroyed here;
+ *   oneka_allreduce_f64    small packed reductions on the same communicator (op: 0 sum, 1 min, 2 max), e.g. the
+ *                          bounding box every rank needs to agree on the lattice.
+ * NCCL is resolved at run time (the libnccl.so.2 already in the process, else the system one; ONEKA_NCCL_LIB
+ * overrides), so the library loads -- and single-GPU use works -- without it.                                    */
+int oneka_comm_unique_id(void *id128_out);
+int oneka_comm_init_rank(oneka_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
+int oneka_comm_attach(oneka_ctx *ctx, void *nccl_comm, int32_t nranks, int32_t rank);
+int oneka_comm_destroy(oneka_ctx *ctx);
+int oneka_allreduce_counts(oneka_ctx *ctx, uint32_t *counts_dev, uint64_t n);
+int oneka_allreduce_f64(oneka_ctx *ctx, double *values_dev, uint64_t n, int32_t op);
+
+/* ---- ProbabilityField.distancesquared on the device (test hook) ------------------------------- *
+ * out_host[n] = distance^2 from c to the segment [a, b] for abc_host[n][6] = ax, ay, bx, by, cx, cy, evaluated by the
+ * very device function the rasteriser uses inside its error band (exact_distancesquared: the operations of
+ * oneka/probabilityfield.py:407-427 in unfused IEEE double).  Bit-exact against the reference.  Synchronous.      */
+int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host, double *out_host);
+
+/* ---- Atomic-throughput probes: the roofline of the rasteriser -------------------------------- *
+ * The rasteriser's memory operation is a bit-set: RED.OR of one 32-bit word per lattice row per segment
+ * (insert(), oneka/probabilityfield.py:296-310 sets rgrid[i, j] node by node).  mode 0: RED.OR to L2, every lane its own
+ * word of a `span_bytes` buffer (uncontended);  mode 1: the same with all 32 lanes of a warp on ONE word (contended);
+ * mode 2: atomicOr on shared memory, every lane its own word;  mode 3: shared memory, one word per warp.
+ * gops_out = 1e9 atomic word-operations per second (best of 5).  Synchronous.                                    */
+int oneka_red_probe(oneka_ctx *ctx, int32_t mode, uint64_t span_bytes, int32_t iters, double *gops_out, double *ms_out);
 
 /* ---- FP64 pipe probe ------------------------------------------------------------------ *
  * Times a register-resident DFMA kernel (no memory traffic) and reports the achieved

@@ -22,6 +22,8 @@ SYMBOLS = [
     "oneka_read_stats", "oneka_reset_stats", "oneka_capture_host", "oneka_fp64_probe", "oneka_path_bboxes",
     "oneka_capture_clipped", "oneka_count_histogram", "oneka_gaussian_smooth", "oneka_capture_guarded",
     "oneka_set_farfield", "oneka_farfield_eval_host", "oneka_set_farfield_unconfined",
+    "oneka_capture_tracked", "oneka_comm_unique_id", "oneka_comm_init_rank", "oneka_comm_attach", "oneka_comm_destroy",
+    "oneka_allreduce_counts", "oneka_allreduce_f64", "oneka_distancesquared_host", "oneka_red_probe",
 ]
 
 
@@ -105,6 +107,16 @@ def load():
     L.oneka_set_farfield_unconfined.argtypes = [_vp, C.c_int]
     L.oneka_farfield_eval_host.argtypes = [C.c_int32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64, _vp, _vp, _vp]
+    L.oneka_capture_tracked.argtypes = [_vp, C.POINTER(ModelDesc), C.POINTER(Lattice), _vp, C.c_int64, C.c_int32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.oneka_comm_unique_id.argtypes = [_vp]
+    L.oneka_comm_init_rank.argtypes = [_vp, C.c_int32, C.c_int32, _vp]
+    L.oneka_comm_attach.argtypes = [_vp, _vp, C.c_int32, C.c_int32]
+    L.oneka_comm_destroy.argtypes = [_vp]
+    L.oneka_allreduce_counts.argtypes = [_vp, _vp, C.c_uint64]
+    L.oneka_allreduce_f64.argtypes = [_vp, _vp, C.c_uint64, C.c_int32]
+    L.oneka_distancesquared_host.argtypes = [_vp, C.c_int64, _vp, _vp]
+    L.oneka_red_probe.argtypes = [_vp, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)                  # AttributeError here = header / library mismatch
     _lib = L

@@ -7,7 +7,10 @@
 #include "oneka_farfield_host.h"
 #include "../../include/oneka_b200.h"
 
+#include <nccl.h>      // types and enums only: the functions are resolved at run time (nccl_api below)
+#include <dlfcn.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <vector>
@@ -68,6 +71,9 @@ struct oneka_ctx {
         unsigned short *near_cnt = nullptr;   // [ntiles]
         double2 *coef = nullptr;              // [realizations of a launch][ntiles][order], grow-only
         size_t coef_bytes = 0;
+        std::vector<double> wells;            // [nw][2] the coordinates the tables were built from (host copy)
+        const void *verified_ptr = nullptr;   // the last well_xy_dev whose contents were compared with `wells` ...
+        bool verified_same = false;           // ... and the outcome (prepare_farfield)
         // unconfined flow (oneka_set_farfield_unconfined)
         bool unconfined = false;
         double *Lg = nullptr;                 // [ntiles][nw] ln |z_w - z_c| of the far wells
@@ -75,6 +81,10 @@ struct oneka_ctx {
         double *b0 = nullptr;                 // [realizations of a launch][ntiles], grow-only
         size_t b0_bytes = 0;
     } ff;
+    // the one collective of the path (oneka_allreduce_counts): communicator owned (comm_init_rank) or borrowed (comm_attach)
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
+    int comm_nranks = 1, comm_rank = 0;
     // profiling
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kind; };
@@ -328,6 +338,51 @@ eval_points_kernel(TrackParams tp, long long npts, const double *pts, double *ou
     }
 }
 
+
+// ProbabilityField.distancesquared (probabilityfield.py:379-427) through the rasteriser's own exact device function
+__global__ void __launch_bounds__(128)
+distsq_kernel(long long n, const double *__restrict__ abc, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *a = abc + 6 * i;
+    out[i] = exact_distancesquared(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
+// Atomic bit-set probes: the memory operation of the rasteriser (one RED.OR per lattice row per segment).
+//   SHARED false: RED.OR.b32 to global memory (resolved in L2), `words` words of target, lane-private or one word per warp
+//   SHARED true : ATOMS.OR on a 32 KB shared-memory tile
+template <bool SHARED, bool CONTENDED>
+__global__ void __launch_bounds__(256)
+red_probe_kernel(unsigned int *buf, unsigned long long words, int iters, unsigned int *sink)
+{
+    __shared__ unsigned int tile[8192];
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned long long gthread = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (SHARED) {
+        for (int i = threadIdx.x; i < 8192; i += blockDim.x) tile[i] = 0u;
+        __syncthreads();
+        unsigned int idx = CONTENDED ? (threadIdx.x >> 5) * 37u : threadIdx.x;
+#pragma unroll 4
+        for (int k = 0; k < iters; ++k) {
+            atomicOr(&tile[idx & 8191u], 1u << ((k + lane) & 31));
+            idx += CONTENDED ? 8u : 256u;                  // a new row of the tile, conflict-free for the lane-private case
+        }
+        __syncthreads();
+        if (tile[threadIdx.x] == 0xdeadbeefu) sink[0] = 1u;  // never true; keeps the tile alive
+        return;
+    }
+    // global: consecutive lanes on consecutive words (the coalesced pattern of neighbouring bitmap words), each warp
+    // walking its own stride through the buffer
+    unsigned long long idx = CONTENDED ? (gthread >> 5) * 32ull : gthread;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x + 4099ull * 32ull;
+#pragma unroll 4
+    for (int k = 0; k < iters; ++k) {
+        atomicOr(buf + (idx % words), 1u << ((k + lane) & 31));   // result unused -> RED.OR
+        idx += step;
+    }
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread, registers only.
 __global__ void __launch_bounds__(256)
 fp64_probe_kernel(int iters, double seed, double *sink)
@@ -510,12 +565,24 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
 
 // Far-field coefficients for the realizations of one launch (rows already offset) -> ctx->ff.coef; fills `out`.
 // Returns ONEKA_OK with use = false when the far field is off or does not apply to this model.
-static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long nr, const double *q, const double *poro,
-                            const double *thick, FarFieldDev &out, bool &use)
+static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long nr, const double *well_xy_dev, const double *q,
+                            const double *poro, const double *thick, FarFieldDev &out, bool &use)
 {
     const oneka_ctx::FarField &f = ctx->ff;
     use = f.on && (m->confined || f.unconfined) && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
     if (!use) return ONEKA_OK;
+    // The tables were built from a HOST copy of the well coordinates (oneka_set_farfield).  A caller that hands over other
+    // wells with the same count and origin must not get near terms from the new coordinates and polynomials from the old
+    // ones: the first time a device pointer is seen its contents are compared with that copy (one small synchronous
+    // read per new pointer, nothing on later launches), and a mismatch means direct sums.
+    if (well_xy_dev != f.verified_ptr) {
+        std::vector<double> now((size_t)f.nw * 2);
+        CUDA_TRY(cudaMemcpyAsync(now.data(), well_xy_dev, now.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->ff.verified_ptr = well_xy_dev;
+        ctx->ff.verified_same = memcmp(now.data(), f.wells.data(), now.size() * sizeof(double)) == 0;
+    }
+    if (!f.verified_same) { use = false; return ONEKA_OK; }
     if (!m->confined && track_smem(f.nw) + (((size_t)f.ntx * f.nty * f.order * 24 + (size_t)f.ntx * f.nty * (10 + 2 * f.max_near) + 15) & ~(size_t)15) > 200 * 1024) {
         use = false;                                                  // the unconfined tables (c64 + p32) do not fit: direct sums
         return ONEKA_OK;
@@ -607,6 +674,49 @@ static double undkey(unsigned long long k)
     return v;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time: the library must load (and single-GPU use must work) without it, and inside a PyTorch
+// process the libnccl.so.2 torch already loaded has to be the one used (two NCCL copies in a process do not share
+// their topology / proxy state).
+struct nccl_api {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+
+static const nccl_api *nccl()
+{
+    static nccl_api api;
+    static int state = 0;                                      // 0 = not tried, 1 = ok, -1 = unavailable
+    if (state == 0) {
+        void *h = nullptr;
+        if (const char *env = getenv("ONEKA_NCCL_LIB")) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // the copy already in the process (torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        state = -1;
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString) state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+
+#define NCCL_TRY(N, expr)                                                                   \
+    do {                                                                                    \
+        ncclResult_t _r = (expr);                                                           \
+        if (_r != ncclSuccess)                                                              \
+            return fail(ONEKA_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, (N)->GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -662,6 +772,7 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->ff.near_idx) cudaFree(ctx->ff.near_idx);
     if (ctx->ff.near_raw) cudaFree(ctx->ff.near_raw);
     if (ctx->ff.b0) cudaFree(ctx->ff.b0);
+    if (ctx->comm && ctx->comm_owned) { if (const nccl_api *N = nccl()) N->CommDestroy(ctx->comm); }
     delete ctx;
 }
 
@@ -732,6 +843,7 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (f.Lg) { cudaFree(f.Lg); f.Lg = nullptr; }
     if (f.near_idx) { cudaFree(f.near_idx); f.near_idx = nullptr; }
     if (f.near_raw) { cudaFree(f.near_raw); f.near_raw = nullptr; }
+    f.wells.clear(); f.verified_ptr = nullptr; f.verified_same = false;
     if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
     FFTables T;
     if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
@@ -754,6 +866,7 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     CUDA_TRY(cudaMemcpy(f.Lg, T.Lg.data(), T.Lg.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_idx, T.idx.data(), T.idx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_raw, T.cnt_raw.data(), T.cnt_raw.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    f.wells.assign(well_xy_host, well_xy_host + (size_t)nw * 2);
     f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.n64 = n64; f.max_near = T.max_near;
     f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
     f.on = true;
@@ -909,7 +1022,7 @@ int oneka_trace(oneka_ctx *ctx, const oneka_model_desc *m, const double *well_xy
     if (farfield_batch(ctx, R) < R) return launch_track<2>(ctx, m, tp, L, nullptr);     // test hook: too many rows for one table
     FarFieldDev ff;
     bool use_ff = false;
-    rc = prepare_farfield(ctx, m, R, q_dev, poro_dev, thick_dev, ff, use_ff);
+    rc = prepare_farfield(ctx, m, R, well_xy_dev, q_dev, poro_dev, thick_dev, ff, use_ff);
     if (rc) return rc;
     return launch_track<2>(ctx, m, tp, L, nullptr, use_ff ? &ff : nullptr);
 }
@@ -988,7 +1101,7 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
         tp.slot_flags = (raster && flags_dev) ? flags_dev + r0 : nullptr;
         FarFieldDev ff;
         bool use_ff = false;
-        rc = prepare_farfield(ctx, m, nr, tp.q, tp.poro, tp.thick, ff, use_ff);
+        rc = prepare_farfield(ctx, m, nr, well_xy_dev, tp.q, tp.poro, tp.thick, ff, use_ff);
         if (rc) return rc;
         if (raster) {
             rc = launch_track<1>(ctx, m, tp, L, ctx->bitmaps, use_ff ? &ff : nullptr);
@@ -1149,6 +1262,163 @@ int oneka_gaussian_smooth(oneka_ctx *ctx, const uint32_t *counts_dev, int32_t nr
     cudaStreamSynchronize(ctx->stream);      // w_host / w_dev lifetime
     cudaFree(w_dev);
     if (e != cudaSuccess) return fail(ONEKA_ERR_CUDA, "gaussian smooth failed: %s", cudaGetErrorString(e));
+    return ONEKA_OK;
+}
+
+int oneka_capture_tracked(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_lattice *lat,
+                          const double *well_xy_dev, int64_t R, int32_t P,
+                          const double *q_dev, const double *cond_dev, const double *poro_dev, const double *thick_dev,
+                          const double *coef_dev, const double *start_xy_dev,
+                          uint32_t *counts_dev, double *end_xy_dev, int32_t *nverts_dev, uint8_t *status_dev,
+                          uint32_t *clipped_dev, double *bbox_dev)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (R == 0) return ONEKA_OK;
+    if (!lat || !counts_dev) return fail(ONEKA_ERR_ARG, "oneka_capture_tracked needs lat and counts_dev");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (clipped_dev) CUDA_TRY(cudaMemsetAsync(clipped_dev, 0, (size_t)R * sizeof(uint32_t), ctx->stream));
+    return capture_impl(ctx, m, lat, well_xy_dev, R, P, q_dev, cond_dev, poro_dev, thick_dev, coef_dev, start_xy_dev,
+                        counts_dev, end_xy_dev, nverts_dev, status_dev, nullptr, bbox_dev, clipped_dev);
+}
+
+// ---- the collective ---------------------------------------------------------------------------
+int oneka_comm_unique_id(void *id128_out)
+{
+    if (!id128_out) return fail(ONEKA_ERR_ARG, "id128_out is NULL");
+    const nccl_api *N = nccl();
+    if (!N) return fail(ONEKA_ERR_NCCL, "NCCL is not available (libnccl.so.2 could not be loaded: %s)", dlerror() ? dlerror() : "no error text");
+    ncclUniqueId id;
+    NCCL_TRY(N, N->GetUniqueId(&id));
+    memcpy(id128_out, &id, sizeof(id));
+    return ONEKA_OK;
+}
+
+int oneka_comm_destroy(oneka_ctx *ctx)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (ctx->comm && ctx->comm_owned) {
+        const nccl_api *N = nccl();
+        if (N) { CUDA_TRY(cudaSetDevice(ctx->device)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); NCCL_TRY(N, N->CommDestroy(ctx->comm)); }
+    }
+    ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_nranks = 1; ctx->comm_rank = 0;
+    return ONEKA_OK;
+}
+
+int oneka_comm_init_rank(oneka_ctx *ctx, int32_t nranks, int32_t rank, const void *id128)
+{
+    if (!ctx || !id128) return fail(ONEKA_ERR_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ONEKA_ERR_ARG, "rank %d of %d", rank, nranks);
+    const nccl_api *N = nccl();
+    if (!N) return fail(ONEKA_ERR_NCCL, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    int rc = oneka_comm_destroy(ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c = nullptr;
+    NCCL_TRY(N, N->CommInitRank(&c, nranks, id, rank));
+    ctx->comm = c; ctx->comm_owned = true; ctx->comm_nranks = nranks; ctx->comm_rank = rank;
+    return ONEKA_OK;
+}
+
+int oneka_comm_attach(oneka_ctx *ctx, void *nccl_comm, int32_t nranks, int32_t rank)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (nccl_comm && !nccl()) return fail(ONEKA_ERR_NCCL, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    int rc = oneka_comm_destroy(ctx);
+    if (rc) return rc;
+    ctx->comm = (ncclComm_t)nccl_comm; ctx->comm_owned = false;
+    ctx->comm_nranks = nccl_comm ? nranks : 1; ctx->comm_rank = nccl_comm ? rank : 0;
+    return ONEKA_OK;
+}
+
+int oneka_allreduce_counts(oneka_ctx *ctx, uint32_t *counts_dev, uint64_t n)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (n == 0) return ONEKA_OK;
+    if (!counts_dev) return fail(ONEKA_ERR_ARG, "counts_dev is NULL");
+    if (!ctx->comm) return fail(ONEKA_ERR_ARG, "no communicator: call oneka_comm_init_rank or oneka_comm_attach first");
+    const nccl_api *N = nccl();
+    if (!N) return fail(ONEKA_ERR_NCCL, "NCCL is not available");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    NCCL_TRY(N, N->AllReduce(counts_dev, counts_dev, (size_t)n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+    return ONEKA_OK;
+}
+
+int oneka_allreduce_f64(oneka_ctx *ctx, double *values_dev, uint64_t n, int32_t op)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    if (n == 0) return ONEKA_OK;
+    if (!values_dev || op < 0 || op > 2) return fail(ONEKA_ERR_ARG, "bad argument to oneka_allreduce_f64");
+    if (!ctx->comm) return fail(ONEKA_ERR_ARG, "no communicator: call oneka_comm_init_rank or oneka_comm_attach first");
+    const nccl_api *N = nccl();
+    if (!N) return fail(ONEKA_ERR_NCCL, "NCCL is not available");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMin : ncclMax);
+    NCCL_TRY(N, N->AllReduce(values_dev, values_dev, (size_t)n, ncclFloat64, o, ctx->comm, ctx->stream));
+    return ONEKA_OK;
+}
+
+int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host, double *out_host)
+{
+    if (!ctx || n < 0 || (n && (!abc_host || !out_host))) return fail(ONEKA_ERR_ARG, "bad argument to oneka_distancesquared_host");
+    if (n == 0) return ONEKA_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)n * 7 * sizeof(double)));
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(buf, abc_host, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        distsq_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, buf, buf + 6 * n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf + 6 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(ONEKA_ERR_CUDA, "oneka_distancesquared_host failed: %s", cudaGetErrorString(e));
+    return ONEKA_OK;
+}
+
+int oneka_red_probe(oneka_ctx *ctx, int32_t mode, uint64_t span_bytes, int32_t iters, double *gops_out, double *ms_out)
+{
+    if (!ctx || mode < 0 || mode > 3 || iters <= 0) return fail(ONEKA_ERR_ARG, "bad argument to oneka_red_probe");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (span_bytes < 4096) span_bytes = 4096;
+    const unsigned long long words = span_bytes / 4;
+    unsigned int *buf = nullptr, *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, words * 4));
+    CUDA_TRY(cudaMalloc(&sink, 4));
+    CUDA_TRY(cudaMemsetAsync(buf, 0, words * 4, ctx->stream));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    auto launch = [&](int it) {
+        switch (mode) {
+        case 0: red_probe_kernel<false, false><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 1: red_probe_kernel<false, true><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 2: red_probe_kernel<true, false><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        default: red_probe_kernel<true, true><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        }
+    };
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    launch(iters / 8 + 1);                                   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(a, ctx->stream));
+        launch(iters);
+        CUDA_TRY(cudaEventRecord(b, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(sink);
+    CUDA_TRY(cudaGetLastError());
+    const double ops = (double)blocks * threads * (double)iters;
+    if (gops_out) *gops_out = ops / (best * 1e-3) / 1e9;
+    if (ms_out) *ms_out = best;
     return ONEKA_OK;
 }
 

@@ -14,6 +14,7 @@ Reference map (file:line under the reference tree):
   Engine.run        the above + choosing the lattice + cropping to the extents the reference's
                     auto-expanding ProbabilityField would end with (probabilityfield.py:229-245)
 """
+import collections
 import ctypes as C
 import functools
 import os
@@ -150,18 +151,21 @@ class Engine:
         torch.cuda.set_device(self.device)
         self._L = _cabi.load()
         self._h = _cabi.create(self.index)
-        self._geom_hint = {}
-        # far-field compression of the well sum (oneka_set_farfield): "auto" = wherever it pays, "off" = direct sums only
+        self._geom_hint = collections.OrderedDict()     # problem key -> (work lattice, far-field box); small LRU
+        self._comm = None                               # (world, rank) once oneka_comm_init_rank has run (init_comm)
+        # far-field compression of the well sum (oneka_set_farfield): "auto" = wherever it pays, "off" = direct sums only,
+        # "force" = wherever it applies, whatever the cost model says (tests, A/B runs)
         self.farfield = "off" if os.environ.get("ONEKA_FARFIELD", "auto").lower() in ("0", "off", "no") else "auto"
         self.farfield_order = int(os.environ.get("ONEKA_FARFIELD_ORDER", "28"))
         self.farfield_eta = float(os.environ.get("ONEKA_FARFIELD_ETA", "0.3"))
         self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "64"))
         self.farfield_order_fp64 = int(os.environ.get("ONEKA_FARFIELD_FP64", "0"))      # 0 = automatic FP64 / FP32 split
         self.farfield_min_wells = 12
-        # opt-in, not yet timed on hardware: the far field for confined=False too (oneka_set_farfield_unconfined)
+        # the far field for confined=False too (oneka_set_farfield_unconfined): on by default since round 2 (measured on
+        # B200: 200 wells 225.9 -> 57.8 ms per 1024 x 1000 paths; 29 wells 119 -> 142 ms, which the cost model of
+        # _auto_farfield declines); ONEKA_FARFIELD_UNCONFINED=0 forces direct sums for unconfined flow
         self._ff_unconfined = False
-        if os.environ.get("ONEKA_FARFIELD_UNCONFINED", "0").lower() in ("1", "on", "yes"):
-            self.farfield_unconfined = True
+        self.farfield_unconfined = os.environ.get("ONEKA_FARFIELD_UNCONFINED", "1").lower() not in ("0", "off", "no")
         self._ff_key = None
         self._ff_info = None
         self.use_stream(torch.cuda.current_stream(self.device))
@@ -171,8 +175,9 @@ class Engine:
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._L.oneka_destroy(self._h)
+            self._L.oneka_destroy(self._h)              # also destroys a communicator the context owns
             self._h = None
+            self._comm = None
 
     def __del__(self):
         try:
@@ -213,6 +218,53 @@ class Engine:
         _cabi.check(self._L.oneka_fp64_probe(self._h, int(iters), C.byref(t), C.byref(ms)))
         return t.value, ms.value
 
+    def red_probe(self, mode, span_bytes=64 << 20, iters=4096):
+        """Atomic bit-set throughput (1e9 word operations/s): mode 0 RED.OR to L2 lane-private words, 1 one word per warp,
+        2 shared-memory atomicOr lane-private, 3 shared memory one word per warp -- the rasteriser's roofline."""
+        g, ms = C.c_double(0), C.c_double(0)
+        _cabi.check(self._L.oneka_red_probe(self._h, int(mode), int(span_bytes), int(iters), C.byref(g), C.byref(ms)))
+        return g.value, ms.value
+
+    def distancesquared(self, abc):
+        """ProbabilityField.distancesquared (oneka/probabilityfield.py:379-427) for rows (ax, ay, bx, by, cx, cy),
+        evaluated by the rasteriser's own exact device function."""
+        abc = np.ascontiguousarray(abc, dtype=np.float64).reshape(-1, 6)
+        out = np.empty(len(abc), dtype=np.float64)
+        _cabi.check(self._L.oneka_distancesquared_host(self._h, len(abc), abc.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- the collective (oneka_allreduce_counts) ------------------------------------------------------
+    def init_comm(self, group):
+        """Join the library's own NCCL communicator over the ranks of `group` (a torch.distributed process group, used
+        only to ship the 128-byte unique id from rank 0).  After this, allreduce_counts() runs through the C ABI on
+        the context's stream.  Collective: every rank of the group must call it."""
+        import torch.distributed as dist
+        torch = self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if self._comm == (world, rank):
+            return
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _cabi.check(self._L.oneka_comm_unique_id(buf))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if hasattr(dist, "get_global_rank") else 0, group=group)
+        idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+        _cabi.check(self._L.oneka_comm_init_rank(self._h, world, rank, idb))
+        self._comm = (world, rank)
+
+    def allreduce_counts(self, counts, group=None):
+        """In-place sum of the per-rank count grids: THE collective of the path (probabilityfield.py:357-358 is additive).
+        Through the C ABI (raw ncclAllReduce of uint32 on the context's stream) once init_comm() has run, else through
+        torch.distributed on `group` (gloo on CPU tensors in the tests)."""
+        if self._comm is not None and self._comm[0] > 1 and counts.is_cuda:
+            if not counts.is_contiguous():
+                raise ValueError("counts must be contiguous")
+            _cabi.check(self._L.oneka_allreduce_counts(self._h, _ptr(counts), counts.numel()))
+            return counts
+        from . import parallel
+        return parallel.allreduce_counts(counts, group)
+
     # -- far-field compression of the well sum ------------------------------------------------------
     def set_farfield(self, spec: Optional[FlowSpec], box=None, order=None, eta=None, max_tiles=None):
         """Configure (or, with spec None, switch off) the tiled far-field expansion for `spec`'s wells on a tile grid
@@ -231,9 +283,13 @@ class Engine:
                                                g["x0"], g["y0"], g["tile"], g["ntx"], g["nty"], order, eta,
                                                int(self.farfield_order_fp64), C.byref(mx), C.byref(mean)))
         info = dict(g, order=order, eta=eta, mean_near=mean.value, max_near=int(mx.value))
-        self._ff_key = (self._ff_wells_key(spec), tuple(float(v) for v in box))
+        self._ff_key = (self._ff_wells_key(spec), tuple(float(v) for v in box), self._ff_settings())
         self._ff_info = info
         return info
+
+    def _ff_settings(self):
+        """The knobs the tables depend on besides wells and box: changing one rebuilds them."""
+        return (int(self.farfield_order), float(self.farfield_eta), int(self.farfield_max_tiles), int(self.farfield_order_fp64))
 
     def _ff_wells_key(self, spec):
         return (len(spec.well_xy), float(spec.xtarget), float(spec.ytarget),
@@ -247,6 +303,8 @@ class Engine:
     def farfield_unconfined(self, on):
         self._ff_unconfined = bool(on)
         _cabi.check(self._L.oneka_set_farfield_unconfined(self._h, int(self._ff_unconfined)))
+        if getattr(self, "_ff_key", None) is not None:        # a remembered "not worth it" may no longer hold
+            self.set_farfield(None)
 
     def _auto_farfield(self, spec: FlowSpec, geom: Optional[LatticeGeom], box=None):
         """Called before every capture: keep / build / drop the far-field tables for this spec and lattice.
@@ -267,13 +325,18 @@ class Engine:
         if box is None:
             box = (geom.xmin, geom.xmax, geom.ymin, geom.ymax)
         box = tuple(float(v) for v in box)
-        key = (wkey, box)
+        key = (wkey, box, self._ff_settings())
         if self._ff_key == key:
             return
         info = self.set_farfield(spec, box)
-        # cost model in well-equivalents (8 FP64 + loads per well): a near well ~1.3, a polynomial term ~0.55
-        cost = 1.3 * (info["mean_near"] + 1.0) + 0.55 * info["order"] + 2.0
-        if cost >= 0.85 * nw:                                       # not worth it: drop the tables, remember the decision
+        # cost model in well-equivalents (8 FP64 + loads per well): a near well ~1.3, a polynomial term ~0.55.  Unconfined
+        # flow pays one more (FP32) Horner for the potential and a dearer near-well term (measured on B200, profiles/r02_*:
+        # 29 wells lose 19 %, 200 wells gain 3.9x)
+        if spec.confined:
+            cost = 1.3 * (info["mean_near"] + 1.0) + 0.55 * info["order"] + 2.0
+        else:
+            cost = 1.7 * (info["mean_near"] + 1.0) + 0.85 * info["order"] + 4.0
+        if cost >= 0.85 * nw and self.farfield != "force":         # not worth it: drop the tables, remember the decision
             _cabi.check(self._L.oneka_set_farfield(self._h, 0, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1, 1, 0, 0.5, 0, None, None))
             self._ff_key, self._ff_info = key, None
 
@@ -385,12 +448,14 @@ class Engine:
         return self.torch.zeros((geom.nrows, geom.ncols), dtype=self.torch.int32, device=self.device)
 
     def capture(self, spec: FlowSpec, dp: DeviceParams, geom: Optional[LatticeGeom] = None, counts=None,
-                per_path=False, r0=0, r1=None, clip=None, flags=None, ff_box=None):
+                per_path=False, r0=0, r1=None, clip=None, flags=None, ff_box=None, bbox_out=None):
         """Enqueue track + rasterise + register for realizations [r0, r1) of `dp` (asynchronous).
 
         geom/counts None -> tracking only.  clip: int32 device tensor [R, P, 4] of per-path raster windows
         (oneka_capture_clipped).  flags: int32 device tensor [R]; realizations that ran off the lattice are
-        flagged and NOT registered (oneka_capture_guarded).  Returns the per-path tensors (or None)."""
+        flagged and NOT registered (oneka_capture_guarded).  bbox_out: float64 device tensor [R, P, 4] that receives
+        every path's bounding box from the same fused pass (oneka_capture_tracked; with or without flags).
+        Returns the per-path tensors (or None)."""
         torch = self.torch
         r1 = dp.R if r1 is None else r1
         R, P = r1 - r0, int(dp.start_xy.shape[0])
@@ -406,7 +471,7 @@ class Engine:
         if nvtx:
             nvtx.range_push("oneka.capture R=%d P=%d %s" % (R, P, "track+raster" if lat is not None else "track"))
         try:
-            self._capture_call(spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags)
+            self._capture_call(spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags, bbox_out)
         finally:
             if nvtx:
                 nvtx.range_pop()
@@ -414,9 +479,21 @@ class Engine:
             return dict(end_xy=end_xy, nverts=nverts, status=status)
         return None
 
-    def _capture_call(self, spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags=None):
+    def _capture_call(self, spec, dp, m, lat, counts, end_xy, nverts, status, clip, r0, r1, R, P, flags=None, bbox_out=None):
         torch = self.torch
-        if flags is not None:
+        if bbox_out is not None:
+            if clip is not None or lat is None or counts is None:
+                raise ValueError("bbox_out needs a lattice and a count grid, and excludes clip")
+            if tuple(bbox_out.shape) != (dp.R, P, 4) or bbox_out.dtype != torch.float64 or not bbox_out.is_contiguous():
+                raise ValueError("bbox_out must be a contiguous float64 tensor [R, P, 4]")
+            if flags is not None and (tuple(flags.shape) != (dp.R,) or flags.dtype != torch.int32 or not flags.is_contiguous()):
+                raise ValueError("flags must be a contiguous int32 tensor [R]")
+            _cabi.check(self._L.oneka_capture_tracked(
+                self._h, C.byref(m), C.byref(lat), _ptr(dp.well_xy), R, P,
+                _ptr(dp.q[r0:r1]), _ptr(dp.cond[r0:r1]), _ptr(dp.poro[r0:r1]), _ptr(dp.thick[r0:r1]), _ptr(dp.coef[r0:r1]),
+                _ptr(dp.start_xy), _ptr(counts), _ptr(end_xy), _ptr(nverts), _ptr(status),
+                _ptr(flags[r0:r1]) if flags is not None else None, _ptr(bbox_out[r0:r1])))
+        elif flags is not None:
             if clip is not None or lat is None or counts is None:
                 raise ValueError("flags needs a lattice and a count grid, and excludes clip")
             if tuple(flags.shape) != (dp.R,) or flags.dtype != torch.int32 or not flags.is_contiguous():
@@ -459,58 +536,164 @@ class Engine:
         from .lattice import clip_windows
         return clip_windows(self.torch, base, final, bb, prior)
 
-    def run_exact(self, spec: FlowSpec, params: RealizationParams, group=None, per_path=False, base: Optional[LatticeGeom] = None):
-        """Like run(), but reproduces the reference's order-dependent clipping exactly: a tracking pass
-        yields every path's bounding box, their running union gives each path the window the reference's
-        grid had at that moment, and the fused pass rasterises with those windows.  Costs one extra
-        tracking pass (~0.6x of a fused pass).  `base`: the caller's existing grid (default: fresh 3 x 3)."""
+    def run_exact(self, spec: FlowSpec, params: RealizationParams, group=None, per_path=False, base: Optional[LatticeGeom] = None,
+                  pilot=256, margin=0.25, pilot_paths=128, reuse_lattice=True, two_pass_below=16):
+        """Like run(), but reproduces the reference's order-dependent clipping exactly (the drop-in default).
+
+        The reference inserts path n into the grid as expanded to the union of the bounding boxes of paths 0..n, in
+        (realization, path) order, and clips every segment's window to THAT grid (probabilityfield.py:298-301, 335).  Once a
+        few realizations have been chronicled that grid covers almost everything that follows, so only a handful of paths
+        -- those whose boxes come within an umbra of the running union's edge -- are clipped at all.  Hence ONE fused pass:
+
+        1. lattice estimate as in run() (pilot or the lattice of the previous call on this problem);
+        2. fused guarded capture that also writes every path's bounding box (oneka_capture_tracked);
+        3. running union of the boxes on the device (cummin / cummax; other ranks' shards come first through one
+           all-gather) -> the grid each path met (lattice.clip_windows) -> the AFFECTED realizations: any path whose
+           box + umbra (+ a cell) is not inside its window, or that ran off the estimated lattice;
+        4. fix-up, affected realizations only: their unclipped contribution is taken out again (the same rows
+           rasterised once more into a scratch grid and subtracted: integer counts, deterministic kernels) and they are
+           rasterised with their exact per-path windows (oneka_capture_clipped).
+        Cost: one fused pass + 2x the affected fraction (~1 % at 10 000 realizations) instead of a tracking pass before the
+        fused one.  With fewer than `two_pass_below` realizations most of them are affected and the two-pass scheme
+        (oneka_path_bboxes, then oneka_capture_clipped for everything) is cheaper; it is also what compute_capturezone uses.
+        `base`: the grid before the first path (default: fresh 3 x 3 on the target, stochastic.py:212)."""
         from . import parallel
+        from .lattice import clip_windows, affected_paths
         torch = self.torch
-        R = len(params)
-        dp = self.upload(spec, params)
-        if base is None:
-            base = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget)
-        self._farfield_from_pilot(spec, params, dp)
-        self.reset_stats()
-        bb = self.path_bboxes(spec, dp)
-        st = self.read_stats()
-        mine = st["bbox"]
-        prior = None
+        R, P = len(params), int(spec.npaths)
+        start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        dp = self.upload(spec, params, start)
+        dev = self.device if group is not None else None
+        rank = 0
         if group is not None:
             import torch.distributed as dist
-            rank, world = dist.get_rank(group), dist.get_world_size(group)
-            t = torch.tensor(list(mine), dtype=torch.float64, device=self.device)
-            allb = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(allb, t, group=group)
-            allb = np.array([b.cpu().numpy() for b in allb])
-            before = allb[:rank]
-            if len(before) and np.isfinite(before).all(axis=1).any():
-                ok = before[np.isfinite(before).all(axis=1)]
-                prior = (ok[:, 0].min(), ok[:, 1].max(), ok[:, 2].min(), ok[:, 3].max())
-            okall = allb[np.isfinite(allb).all(axis=1)]
-            true_bbox = (okall[:, 0].min(), okall[:, 1].max(), okall[:, 2].min(), okall[:, 3].max())
-        else:
-            true_bbox = mine
-        if parallel.sum_int(R, group, self.device if group is not None else None) == 0:
+            rank = dist.get_rank(group)
+        if base is None:
+            base = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget)
+        key = self._problem_key(spec)
+        hint = self._hint_get(key) if reuse_lattice else None
+
+        # ---- small runs: two passes (every realization would be "affected" anyway) ----
+        g0 = parallel.gather_rows([R], group, dev)
+        total = int(g0[:, 0].sum())
+        if total == 0:
             return self._empty_result(spec, base)
+        if total < two_pass_below:
+            self._farfield_from_pilot(spec, params, dp)
+            self.reset_stats()
+            bb = self.path_bboxes(spec, dp) if R else torch.empty((0, P, 4), dtype=torch.float64, device=self.device)
+            mine = self.read_stats()["bbox"]
+            allb = parallel.gather_rows(mine, group, dev)
+            prior = parallel.union_bbox(allb[:rank]) if rank else None
+            true_bbox = parallel.union_bbox(allb)
+            if not np.all(np.isfinite(true_bbox)):
+                raise OnekaError("non-finite bounding box %r" % (true_bbox,))
+            final = base.expanded(*true_bbox)
+            clip = clip_windows(torch, base, final, bb, prior)
+            del bb
+            counts = self.new_counts(final)
+            self.reset_stats()
+            pp = self.capture(spec, dp, final, counts, per_path=per_path, clip=clip) if R else None
+            stats = self.read_stats()
+            stats["affected_realizations"] = R
+            if group is not None:
+                self.allreduce_counts(counts, group)
+            out = _to_host(counts).view(np.uint32)
+            if per_path and pp is not None:
+                pp = {k: _to_host(v) for k, v in pp.items()}
+            return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=final)
+
+        # ---- 1. lattice estimate ----
+        self.reset_stats()
+        if hint is None:
+            if R > 0:
+                rstep = max(1, R // max(1, pilot))
+                pstep = max(1, spec.npaths // max(1, pilot_paths))
+                if rstep == 1 and pstep == 1:
+                    self.capture(spec, dp)
+                else:
+                    self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
+            bbox = parallel.union_bbox(parallel.gather_rows(self.read_stats()["bbox"], group, dev))
+            if not np.all(np.isfinite(bbox)):
+                raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
+            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+            pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
+            work = base.expanded(bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+            ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
+        else:
+            work, ff_box = hint
+            if work.deltax != base.deltax or work.deltay != base.deltay:
+                raise OnekaError("internal: lattice hint of another spacing")
+            work = work.expanded(base.xmin + 0.5 * base.deltax, base.xmax - 0.5 * base.deltax,
+                                 base.ymin + 0.5 * base.deltay, base.ymax - 0.5 * base.deltay)      # the base grid is part of the result
+
+        # ---- 2. ONE fused pass: count grid + per-path boxes; realizations that leave `work` are flagged, not registered ----
+        counts = self.new_counts(work)
+        flags = torch.zeros(R, dtype=torch.int32, device=self.device)
+        bb = torch.empty((R, P, 4), dtype=torch.float64, device=self.device)
+        self.reset_stats()
+        pp = self.capture(spec, dp, work, counts, per_path=per_path, flags=flags, ff_box=ff_box, bbox_out=bb) if R else None
+        stats = self.read_stats()
+
+        # ---- 3. the grid each path met ----
+        allb = parallel.gather_rows(stats["bbox"], group, dev)
+        prior = parallel.union_bbox(allb[:rank]) if rank else None
+        true_bbox = parallel.union_bbox(allb)
         if not np.all(np.isfinite(true_bbox)):
             raise OnekaError("non-finite bounding box %r" % (true_bbox,))
         final = base.expanded(*true_bbox)
-        clip = self.clip_windows(base, final, bb, prior)
-        del bb
-        counts = self.new_counts(final)
-        self.reset_stats()
-        pp = self.capture(spec, dp, final, counts, per_path=per_path, clip=clip)
-        stats = self.read_stats()
+        nflag = naff = 0
+        if R:
+            clip = clip_windows(torch, base, final, bb, prior)
+            aff_path = affected_paths(torch, final, bb, clip, spec.umbra)
+            aff = aff_path.any(dim=1) | (flags != 0)
+            redo = aff.nonzero().reshape(-1)                       # affected realizations, in order
+            undo = (aff & (flags == 0)).nonzero().reshape(-1)      # ... of which these were registered in pass 2
+            nflag, naff = int((flags != 0).sum().item()), int(redo.numel())
+            del bb, aff_path
+        stats["rerun_realizations"] = nflag
+        stats["affected_realizations"] = naff
+
+        # ---- 4. fix-up ----
+        if R and int(undo.numel()):
+            minus = self.new_counts(work)
+            self.capture(spec, dp.select(undo), work, minus, ff_box=ff_box)
+            counts -= minus
+            del minus
+        out_grid = self.new_counts(final)
+        _copy_overlap(counts, work, out_grid, final)
+        del counts
+        if R and naff:
+            self.capture(spec, dp.select(redo), final, out_grid, clip=clip.index_select(0, redo).contiguous(), ff_box=ff_box)
         if group is not None:
-            parallel.allreduce_counts(counts, group)
-            total = parallel.sum_int(R, group, self.device)
-        else:
-            total = R
-        out = _to_host(counts).view(np.uint32)
-        if per_path:
+            self.allreduce_counts(out_grid, group)
+        out = _to_host(out_grid).view(np.uint32)
+        if per_path and pp is not None:
             pp = {k: _to_host(v) for k, v in pp.items()}
-        return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=final)
+        if reuse_lattice:
+            tb = true_bbox
+            pw, ph = margin * max(tb[1] - tb[0], spec.umbra), margin * max(tb[3] - tb[2], spec.umbra)
+            keep = work if nflag == 0 else work.expanded(tb[0] - pw, tb[1] + pw, tb[2] - ph, tb[3] + ph)
+            self._hint_put(key, (keep, ff_box))
+        return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=work)
+
+    # -- lattice hints: a small LRU keyed by the problem (ADVICE r1: bounded, and replaced when it proved too small) ----
+    @staticmethod
+    def _problem_key(spec):
+        return (spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths, spec.duration, spec.spacing, spec.umbra, spec.confined,
+                spec.tol, spec.maxstep, np.ascontiguousarray(spec.well_xy, dtype=np.float64).tobytes())
+
+    def _hint_get(self, key):
+        hint = self._geom_hint.get(key)
+        if hint is not None:
+            self._geom_hint.move_to_end(key)
+        return hint
+
+    def _hint_put(self, key, value, cap=8):
+        self._geom_hint[key] = value
+        self._geom_hint.move_to_end(key)
+        while len(self._geom_hint) > cap:
+            self._geom_hint.popitem(last=False)
 
     # -- the hot path, host buffers in / host grid out (what the drop-in layer calls) -------------
     def capture_host(self, spec: FlowSpec, params: RealizationParams, geom: Optional[LatticeGeom], start_xy=None,
@@ -572,27 +755,29 @@ class Engine:
         start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
         dp = self.upload(spec, params, start)
         dev = self.device if group is not None else None
+        # Between the kernel phases the ranks have to agree on a few numbers (bounding box, realization count, whether any
+        # realization was flagged): each agreement is ONE all-gather of a packed vector (parallel.gather_rows) -- two of
+        # them without a lattice hint, one with -- plus the one allreduce of the count grid.
         # 1. pilot (skipped when this engine has already seen the same problem: the lattice of the previous call is
         #    reused as the estimate -- chunked runs of one problem pay for the pilot once; the guarded capture below
         #    makes a poor estimate cost a partial re-run, never a wrong grid)
-        key = (spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths, spec.duration, spec.spacing, spec.umbra, spec.confined,
-               spec.tol, spec.maxstep, spec.well_xy.tobytes())
-        hint = self._geom_hint.get(key) if reuse_lattice else None      # every rank makes the same calls, so the caches agree
+        key = self._problem_key(spec)
+        hint = self._hint_get(key) if reuse_lattice else None          # every rank makes the same calls, so the caches agree
         self.reset_stats()
-        if R > 0 and hint is None:
-            rstep = max(1, R // max(1, pilot))
-            pstep = max(1, spec.npaths // max(1, pilot_paths))
-            if rstep == 1 and pstep == 1:
-                self.capture(spec, dp)
-            else:
-                self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
-        if parallel.sum_int(R, group, dev) == 0:
-            return self._empty_result(spec)              # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
-        # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
         if hint is not None:
             geom, ff_box = hint
         else:
-            bbox = parallel.reduce_bbox(self.read_stats()["bbox"], group, dev)
+            if R > 0:
+                rstep = max(1, R // max(1, pilot))
+                pstep = max(1, spec.npaths // max(1, pilot_paths))
+                if rstep == 1 and pstep == 1:
+                    self.capture(spec, dp)
+                else:
+                    self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
+            g1 = parallel.gather_rows(list(self.read_stats()["bbox"]) + [R], group, dev)
+            if int(g1[:, 4].sum()) == 0:
+                return self._empty_result(spec)          # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
+            bbox = parallel.union_bbox(g1[:, :4])
             if not np.all(np.isfinite(bbox)):
                 raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
             w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
@@ -601,16 +786,21 @@ class Engine:
                 bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
             # far-field tiles cover where the particles are (pilot box + 10 %), not the lattice's safety margin
             ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
+        # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
         work_geom = geom
         counts = self.new_counts(geom)
         flags = self.torch.zeros(R, dtype=self.torch.int32, device=self.device)
         self.reset_stats()
-        pp = self.capture(spec, dp, geom, counts, per_path=per_path, flags=flags, ff_box=ff_box)
+        pp = self.capture(spec, dp, geom, counts, per_path=per_path, flags=flags, ff_box=ff_box) if R else None
         stats = self.read_stats()
-        true_bbox = parallel.reduce_bbox(stats["bbox"], group, dev)
         nflag = int(flags.sum().item()) if R else 0
+        g2 = parallel.gather_rows(list(stats["bbox"]) + [R, nflag], group, dev)
+        total = int(g2[:, 4].sum())
+        if total == 0:
+            return self._empty_result(spec)
+        true_bbox = parallel.union_bbox(g2[:, :4])
         stats["rerun_realizations"] = nflag
-        rerun = parallel.any_rank(nflag > 0, group, dev)
+        rerun = bool(g2[:, 5].sum() > 0)
         if rerun:
             # ... and only those are tracked again, on the exact final extents; pass-1 counts are carried over
             final = final_geometry(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget, true_bbox)
@@ -622,17 +812,21 @@ class Engine:
         elif not geom.strictly_contains(true_bbox):
             raise OnekaError("internal: a vertex left the lattice but no realization was flagged")
         if group is not None:
-            parallel.allreduce_counts(counts, group)
-            total = parallel.sum_int(R, group, self.device)
-        else:
-            total = R
+            self.allreduce_counts(counts, group)
         final = final_geometry(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget, true_bbox)
         i0, j0 = geom.offset_of(final)
         out = _to_host(counts[i0:i0 + final.nrows, j0:j0 + final.ncols]).view(np.uint32)
-        if per_path:
+        if per_path and pp is not None:
             pp = {k: _to_host(v) for k, v in pp.items()}
-        if reuse_lattice and not rerun:
-            self._geom_hint[key] = (work_geom, ff_box)   # it fitted every realization: a good estimate for the next call
+        if reuse_lattice:
+            if not rerun:
+                self._hint_put(key, (work_geom, ff_box))     # it fitted every realization: a good estimate for the next call
+            else:
+                # it proved too small: the next call starts from the larger of the two (old work lattice grown to the
+                # true extents plus the margin), so the partial re-run is not repeated call after call
+                tb = true_bbox
+                pw, ph = margin * max(tb[1] - tb[0], spec.umbra), margin * max(tb[3] - tb[2], spec.umbra)
+                self._hint_put(key, (work_geom.expanded(tb[0] - pw, tb[1] + pw, tb[2] - ph, tb[3] + ph), ff_box))
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
 
 

@@ -80,15 +80,16 @@ def compute_capturezone(xtarget, ytarget, rtarget, npaths, duration, pfield, umb
     eng = default_engine()
     spec, par = _spec_and_params(mo, confined, xtarget, ytarget, rtarget, npaths, duration,
                                  pfield.deltax, umbra, tol, maxstep)
-    if pfield.nrows == 0 or pfield.ncols == 0:
-        raise ValueError("compute_capturezone needs a ProbabilityField anchored on the target (stochastic.py:212)")
-    if pfield.deltax != pfield.deltay:
-        raise ValueError("the kernels take one spacing; deltax must equal deltay (stochastic.py:212 always passes spacing twice)")
     start = start_ring(xtarget, ytarget, rtarget, npaths)
     dp = eng.upload(spec, par, start)
     eng.reset_stats()
     bb = eng.path_bboxes(spec, dp)                          # tracking only
     bbox = eng.read_stats()["bbox"]
+    if pfield.nrows == 0 or pfield.ncols == 0:
+        # un-anchored field: the reference's rasterize() of the FIRST trace takes expand()'s empty-field branch
+        # (probabilityfield.py:205-220), which puts that trace's (min x, min y) at node [1, 1]; every later trace grows it
+        b0 = bb[0, 0].cpu().numpy()
+        pfield.expand(float(b0[0]), float(b0[1]), float(b0[2]), float(b0[3]))
     base = LatticeGeom.of_field(pfield)
     pfield.expand(bbox[0], bbox[1], bbox[2], bbox[3])       # union of the per-trace expands (:335)
     geom = LatticeGeom.of_field(pfield)

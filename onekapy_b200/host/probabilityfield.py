@@ -15,6 +15,10 @@ from ..lattice import LatticeGeom
 
 
 class ProbabilityField:
+    # Pickles written by the reference's archive (oneka/archive.py:46-89: a bz2-compressed pickle of a dict whose 'pfield'
+    # entry is this object) name the class `oneka.probabilityfield.ProbabilityField`; the drop-in module `oneka.probabilityfield`
+    # re-exports this class, so archives written here load in the reference and vice versa (tests/test_archive_roundtrip.py).
+    __module__ = "oneka.probabilityfield"
 
     def __init__(self, deltax, deltay, xo=np.nan, yo=np.nan):
         """oneka/probabilityfield.py:125-151."""

@@ -127,3 +127,22 @@ def clip_windows(torch, base, final, bb, prior=None):
     bottom = i0 - cells_below(base.ymin, lo_y, base.deltay)
     top = i0 + base.nrows + cells_above(base.ymax, hi_y, base.deltay)
     return torch.stack([left, right, bottom, top], dim=1).to(torch.int32).reshape(R, P, 4).contiguous()
+
+
+def affected_paths(torch, final, bb, clip, umbra):
+    """bool [R, P]: could the reference's grid-at-that-moment have clipped ANY segment window of the path?
+
+    insert() needs, for a segment, the nodes floor((min - umbra - xmin)/delta) .. floor((max + umbra - xmin)/delta)
+    (probabilityfield.py:298-301); every segment of a path lies inside the path's bounding box, so its windows lie
+    inside the box's window.  A path whose box window, widened by ONE MORE cell on every side (the floors here are not
+    the reference's operation-for-operation floors), sits inside its clip window was rasterised exactly as the
+    reference did even without the clip.  Conservative by construction: a path wrongly called affected only costs time.
+    bb: float64 [R, P, 4] (min x, max x, min y, max y); clip: int32 [R, P, 4] from clip_windows (indices of `final`)."""
+    u = float(umbra)
+    c = clip.to(torch.float64)
+    need_l = torch.floor((bb[..., 0] - u - final.xmin) / final.deltax) - 1.0
+    need_r = torch.floor((bb[..., 1] + u - final.xmin) / final.deltax) + 2.0        # half-open upper end + one cell
+    need_b = torch.floor((bb[..., 2] - u - final.ymin) / final.deltay) - 1.0
+    need_t = torch.floor((bb[..., 3] + u - final.ymin) / final.deltay) + 2.0
+    inside = (need_l >= c[..., 0]) & (need_r <= c[..., 1]) & (need_b >= c[..., 2]) & (need_t <= c[..., 3])
+    return ~inside                                               # (a nan box compares false everywhere -> affected)

@@ -5,7 +5,9 @@ reference's loop is the additive grid and total_weight (oneka/probabilityfield.p
 so the path shards by realization index with no exchange until the end:
 
   * shard_range        contiguous slice of [0, R) per rank
-  * allreduce_counts   the single NCCL allreduce(sum) of the integer count grid over NVLink
+  * allreduce_counts   the single allreduce(sum) of the integer count grid (torch.distributed form: gloo on CPU in the tests;
+                       on GPUs Engine.allreduce_counts issues the same sum through the C ABI, oneka_allreduce_counts)
+  * gather_rows        one all-gather of a short packed vector (bounding box, counts) between kernel phases
   * reduce_bbox        4 doubles min/max, so that every rank works on the same lattice
 
 Counts are integers, so the reduced grid is order-independent and bit-reproducible for any
@@ -59,6 +61,31 @@ def sum_int(value, group=None, device=None):
     t = torch.tensor([int(value)], dtype=torch.int64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t.item())
+
+
+def gather_rows(values, group=None, device=None):
+    """All ranks' copies of a short float64 vector -> ndarray [world, n] (ONE collective, one host read).
+
+    Engine.run packs everything the ranks have to agree on between two kernel phases (bounding box, realization count,
+    number of flagged realizations) into one such vector instead of issuing a blocking scalar collective per item."""
+    v = np.asarray(values, dtype=np.float64).reshape(-1)
+    if group is None:
+        return v[None, :].copy()
+    import torch
+    dist = _dist()
+    t = torch.as_tensor(v, dtype=torch.float64).to(device or "cpu")
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return torch.stack(out).cpu().numpy()
+
+
+def union_bbox(rows):
+    """(min x, max x, min y, max y) over the finite rows of [n, 4]; all-infinite when there is none."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 4)
+    ok = rows[np.isfinite(rows).all(axis=1)]
+    if len(ok) == 0:
+        return (np.inf, -np.inf, np.inf, -np.inf)
+    return (float(ok[:, 0].min()), float(ok[:, 1].max()), float(ok[:, 2].min()), float(ok[:, 3].max()))
 
 
 def allreduce_counts(counts, group=None):

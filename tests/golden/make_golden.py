@@ -20,6 +20,8 @@ recorded inputs are stored, as small .npz files:
   sto_perham.npz     same for data/perham.py, 2 x 20
   unc_basic.npz      confined=False path, 3 x 8 (+ a trace that raises AquiferError)
   fwd_basic.npz      negative duration (forward tracking) from injection wells (data/basic.py, discharges negated)
+  archive_ref.bz2    oneka/archive.py dump_oneka executed on a 2 x 6 run of data/basic.py (+ archive_ref_pgrid.npz)
+  unanchored.npz     compute_capturezone on an UN-anchored field with deltax != deltay (expand()'s empty-field branch), 2 x 7
   sto_wells200.npz   the stochastic path on this repo's synthetic 200-well field (onekapy_b200/synthetic.py), 1 x 10: the
                      executed reference on a field large enough for the far-field compression to carry most of the wells
 
@@ -383,10 +385,63 @@ def gen_unconfined_dry():
     print("   dry traces: vertices", np.diff(off), "terminated early:", flags)
 
 
+def gen_archive():
+    """oneka/archive.py:46-85 EXECUTED: dump_oneka writes 'logs\\Oneka<timestamp>.bz2' (a Windows-style name) into the
+    working directory; the file is moved here as archive_ref.bz2, its pgrid kept beside it for the loading test."""
+    import glob
+    import shutil
+    import tempfile
+    from oneka.archive import dump_oneka, load_oneka
+    m = importlib.import_module("data.basic")
+    par = sample_params(m, 2, 41)
+    pf, _ = run_reference(m, par, 6, m.CONFINED)
+    obs = filter_obs(m.OBSERVATIONS, m.WELLS, m.BUFFER)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    try:
+        os.chdir(tmp)
+        dump_oneka("golden", 1.0, m.TARGET, 6, m.DURATION, 2, m.BASE, m.C_DIST, m.P_DIST, m.T_DIST, m.WELLS, obs,
+                   m.BUFFER, m.SPACING, m.UMBRA, m.SMOOTH, m.CONFINED, m.TOL, m.MAXSTEP, pf)
+        (made,) = glob.glob(os.path.join(tmp, "*Oneka*.bz2"))
+        back = load_oneka(made)
+        assert np.array_equal(back["pfield"].pgrid, pf.pgrid)
+        shutil.move(made, os.path.join(HERE, "archive_ref.bz2"))
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "archive_ref_pgrid.npz"), pgrid=pf.pgrid.astype(np.uint16))
+    print("archive_ref.bz2    %8.1f KiB (grid %dx%d, total_weight %.0f)" % (os.path.getsize(os.path.join(HERE, "archive_ref.bz2")) / 1024.0,
+                                                                         pf.nrows, pf.ncols, pf.total_weight))
+
+
+def gen_unanchored():
+    """compute_capturezone on a caller-owned field that is NOT anchored (ProbabilityField(dx, dy), nrows = ncols = 0) and
+    has deltax != deltay: the first trace's rasterize() takes expand()'s empty-field branch (probabilityfield.py:205-220)."""
+    m = importlib.import_module("data.basic")
+    par = sample_params(m, 2, 53)
+    xt, yt, rt = m.WELLS[m.TARGET][0:3]
+    dx, dy, npaths = 10.0, 6.0, 7
+    pf = ProbabilityField(dx, dy)
+    with TraceRecorder() as rec:
+        for i in range(2):
+            wells = [[w[0], w[1], w[2], par["q"][i, j]] for j, w in enumerate(m.WELLS)]
+            mo = Model(m.BASE, par["k"][i], par["n"][i], par["H"][i], wells)
+            mo.xo, mo.yo = xt, yt
+            mo.coef = par["coef"][i]
+            ref_cz.compute_capturezone(xt, yt, rt, npaths, m.DURATION, pf, m.UMBRA, 1.0, m.TOL, m.MAXSTEP, make_feval(mo, True))
+    off, verts = pack_traces(rec.traces)
+    out = dict(q=par["q"], k=par["k"], n=par["n"], H=par["H"], coef=par["coef"],
+               wells_xyr=np.array([[w[0], w[1], w[2]] for w in m.WELLS], dtype=float),
+               scal=np.array([xt, yt, rt, npaths, m.DURATION, dx, dy, m.UMBRA, m.TOL, m.MAXSTEP, m.BASE]), offsets=off, verts=verts)
+    out.update(field_dict(pf, "auto_"))
+    save("unanchored.npz", **out)
+    print("   unanchored field %g x %g: grid %dx%d nonzero %d" % (dx, dy, pf.nrows, pf.ncols, np.count_nonzero(pf.pgrid)))
+
+
 if __name__ == "__main__":
     import logging
     logging.disable(logging.CRITICAL)
-    which = sys.argv[1:] or ["points", "fit", "distsq", "expand", "insert", "det", "sto", "perham", "unc", "fwd", "dry", "wells200"]
+    which = sys.argv[1:] or ["points", "fit", "distsq", "expand", "insert", "det", "sto", "perham", "unc", "fwd", "dry", "wells200",
+                             "archive", "unanchored"]
     if "points" in which:
         gen_model_points()
     if "fit" in which:
@@ -409,5 +464,9 @@ if __name__ == "__main__":
         gen_capture("fwd_basic.npz", "basic", 2, 6, seed=21, duration=-1500.0, injection=True)
     if "dry" in which:
         gen_unconfined_dry()
+    if "archive" in which:
+        gen_archive()
+    if "unanchored" in which:
+        gen_unanchored()
     if "wells200" in which:
         gen_capture("sto_wells200.npz", synthetic_module(200), 1, 10, seed=31)

@@ -235,6 +235,83 @@ def test_exact_clip_pipeline_equals_auto_expanding_reference(golden, name):
     assert np.count_nonzero(out["counts"] != want) == 0
 
 
+@pytest.mark.parametrize("shards", [1, 2])
+@pytest.mark.parametrize("name", ["sto_basic.npz", "sto_perham.npz", "fwd_basic.npz", "det_basic.npz", "unc_basic.npz", "sto_wells200.npz"])
+def test_one_pass_exact_clip_pipeline(golden, name, shards):
+    """Engine.run_exact's ONE-PASS scheme with the device code on the CPU (same host logic: lattice.clip_windows,
+    lattice.affected_paths): fused unclipped pass that also yields every path's box -> running union -> affected
+    realizations -> their unclipped contribution subtracted, their clipped contribution added == the executed reference's
+    auto-expanding grid, cell for cell; with 2 shards, shard 1's paths come after shard 0's (its windows start from
+    shard 0's box) and the grids are summed -- what the allreduce does across GPUs."""
+    import torch
+    from onekapy_b200.lattice import clip_windows, affected_paths
+    g = golden(name)
+    s, spec, par = spec_of(g)
+    ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
+    base = LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"])
+    R = len(par)
+    cuts = [0, R] if shards == 1 or R < 2 else [0, (R + 1) // 2, R]
+    # a generous work lattice (what the pilot + margin provides)
+    v = g["verts"]
+    work = base.expanded(v[:, 0].min() - 60.0, v[:, 0].max() + 60.0, v[:, 1].min() - 60.0, v[:, 1].max() + 60.0)
+    passA, boxes = [], []
+    for r0, r1 in zip(cuts, cuts[1:]):
+        out = emu.capture(spec, par.slice(r0, r1), ring, 1, geom=work, path_bbox=True)
+        assert out["stats"]["n_clipped"] == 0
+        passA.append(out)
+        boxes.append(out["stats"]["bbox"])
+    true_bbox = (min(b[0] for b in boxes), max(b[1] for b in boxes), min(b[2] for b in boxes), max(b[3] for b in boxes))
+    final = base.expanded(*true_bbox)
+    ref = g["auto_geom"]
+    assert [final.xmin, final.xmax, final.ymin, final.ymax, final.nrows, final.ncols] == list(ref[[0, 1, 2, 3, 6, 7]])
+    i0, j0 = work.offset_of(final)
+    total = np.zeros((final.nrows, final.ncols), dtype=np.int64)
+    naff = 0
+    for k, (r0, r1) in enumerate(zip(cuts, cuts[1:])):
+        prior = None
+        if k:
+            pb = boxes[:k]
+            prior = (min(b[0] for b in pb), max(b[1] for b in pb), min(b[2] for b in pb), max(b[3] for b in pb))
+        bb = torch.from_numpy(passA[k]["path_bbox"])
+        clip = clip_windows(torch, base, final, bb, prior)
+        aff = affected_paths(torch, final, bb, clip, s["umbra"]).any(dim=1).numpy()
+        idx = np.nonzero(aff)[0]
+        naff += len(idx)
+        counts = passA[k]["counts"].astype(np.int64)
+        if len(idx):
+            sub = RealizationParams(q=par.q[r0:r1][idx], cond=par.cond[r0:r1][idx], poro=par.poro[r0:r1][idx],
+                                    thick=par.thick[r0:r1][idx], coef=par.coef[r0:r1][idx])
+            minus = emu.capture(spec, sub, ring, 1, geom=work)["counts"]
+            counts -= minus
+        assert counts.min() >= 0
+        assert counts.sum() == counts[i0:i0 + final.nrows, j0:j0 + final.ncols].sum()      # nothing is left outside the final extents
+        total += counts[i0:i0 + final.nrows, j0:j0 + final.ncols]
+        if len(idx):
+            total += emu.capture(spec, sub, ring, 1, geom=final, clip=clip.numpy()[idx])["counts"]
+    want = g["auto_counts"].astype(np.int64)
+    assert total.shape == want.shape and np.count_nonzero(total != want) == 0
+    assert naff >= 1                                             # the very first paths always meet a grid still growing
+
+
+def test_affected_paths_is_conservative_and_selective():
+    """lattice.affected_paths on synthetic boxes: a path deep inside its window is not affected, one within umbra + a cell
+    of the window's edge is; nan boxes count as affected."""
+    import torch
+    from onekapy_b200.lattice import affected_paths
+    final = LatticeGeom.anchored(4.0, 4.0, 0.0, 0.0).expanded(-400.0, 400.0, -400.0, 400.0)
+    i0 = int(round((0.0 - final.ymin) / 4.0))
+    j0 = int(round((0.0 - final.xmin) / 4.0))
+    win = [j0 - 50, j0 + 51, i0 - 50, i0 + 51]                    # nodes -200 .. 200 in both directions
+    bb = torch.tensor([[[-150.0, 150.0, -150.0, 150.0],           # inside with 50 m to spare
+                        [-190.0, 150.0, -150.0, 150.0],           # 10 m from the left edge: umbra 8 + 4 m of cell -> affected
+                        [-150.0, 150.0, -150.0, 192.5],           # top: node 50 is needed (192.5 + 8 > 200), + a cell of slack > window 
+                        [-150.0, 150.0, -150.0, 180.0],           # top: 20 m to spare -> fine
+                        [float("nan"), 1.0, 0.0, 1.0]]], dtype=torch.float64)
+    clip = torch.tensor([[win] * 5], dtype=torch.int32)
+    got = affected_paths(torch, final, bb, clip, 8.0)[0].tolist()
+    assert got == [False, True, True, False, True]
+
+
 def test_unconfined_far_field_vs_direct_and_oracle():
     """field_feval_ff_unc (opt-in, oneka_set_farfield_unconfined): the perham and 200-well fields with confined=False --
     thick aquifers (saturated nowhere near the wells: the FP64 fallback runs) and thin ones (saturated everywhere: the FP32

@@ -173,8 +173,16 @@ def test_engine_far_field_policy_without_a_gpu():
     e._auto_farfield(spec, geom)                                   # unconfined: direct unless opted in
     assert e.farfield_info() is None and e._L.calls[-1] == ("set", 0, 0)
     e.farfield_unconfined = True
+    e._auto_farfield(spec, geom)                                   # 29 wells, unconfined: the dearer evaluation does not pay
+    assert e._L.calls[-3:] == [("unconfined", 1), ("set", 29, 28), ("set", 0, 0)] and e.farfield_info() is None
+    e.farfield = "force"                                           # ... unless forced (tests, A/B runs)
+    e._ff_key = None
     e._auto_farfield(spec, geom)
-    assert e._L.calls[-2:] == [("unconfined", 1), ("set", 29, 28)] and e.farfield_info() is not None
+    assert e._L.calls[-1] == ("set", 29, 28) and e.farfield_info() is not None
+    e.farfield = "auto"
+    big = FlowSpec(**{**spec.__dict__, "well_xy": np.concatenate([wxy + 7.0 * k for k in range(7)])})    # 203 wells
+    e._auto_farfield(big, geom)
+    assert e._L.calls[-1] == ("set", 203, 28) and e.farfield_info() is not None
     # too many near wells (cost model): tables built, measured, dropped -- and the decision remembered
     e2 = _stub_engine(25.0)
     spec.confined = True

@@ -373,13 +373,29 @@ def test_run_vs_auto_expanding_reference(eng, golden, name):
     assert frac < 2e-2
 
 
+@pytest.mark.parametrize("scheme", ["two_pass", "one_pass", "one_pass_tight_lattice", "one_pass_hint"])
 @pytest.mark.parametrize("name", CAPTURES)
-def test_run_exact_equals_auto_expanding_reference(eng, golden, name):
+def test_run_exact_equals_auto_expanding_reference(eng, golden, name, scheme):
     """Engine.run_exact reproduces the reference's order-dependent clipping: the grid of the executed reference,
-    left auto-expanding, cell for cell."""
+    left auto-expanding, cell for cell -- by the two-pass scheme (small runs: bounding-box pass, then everything clipped)
+    and by the one-pass scheme (fused pass with per-path boxes, then only the affected realizations taken out and
+    re-rasterised with their windows), the latter also on a lattice estimate that is too small (flagged realizations)
+    and on a second call that reuses the lattice."""
     g = golden(name)
     s, spec, par = spec_of(g)
-    res = eng.run_exact(spec, par)
+    if scheme == "two_pass":
+        res = eng.run_exact(spec, par, two_pass_below=10**9)
+        assert res["stats"]["affected_realizations"] == len(par)
+    elif scheme == "one_pass":
+        res = eng.run_exact(spec, par, two_pass_below=0, reuse_lattice=False)
+        assert 1 <= res["stats"]["affected_realizations"] <= len(par) and res["stats"]["rerun_realizations"] == 0
+    elif scheme == "one_pass_tight_lattice":
+        res = eng.run_exact(spec, par, two_pass_below=0, reuse_lattice=False, pilot=1, pilot_paths=2, margin=0.0)
+    else:
+        eng.run_exact(spec, par, two_pass_below=0)
+        n0 = eng.launch_count()
+        res = eng.run_exact(spec, par, two_pass_below=0)
+        assert res["stats"]["rerun_realizations"] == 0
     ref = geom(g, "auto_")
     gm = res["geom"]
     assert (gm.xmin, gm.xmax, gm.ymin, gm.ymax, gm.nrows, gm.ncols) == (ref["xmin"], ref["xmax"], ref["ymin"], ref["ymax"], ref["nrows"], ref["ncols"])

@@ -47,6 +47,11 @@ def _worker(rank, world, port, out_dir):
     local_bbox = (pf.xmin + pf.deltax, pf.xmax - pf.deltax, pf.ymin + pf.deltay, pf.ymax - pf.deltay) if r1 > r0 \
         else (np.inf, -np.inf, np.inf, -np.inf)
     bbox = parallel.reduce_bbox(local_bbox, group)
+    # the packed form Engine.run / run_exact use: ONE all-gather of (bbox, R, flag count) per agreement
+    rows = parallel.gather_rows(list(local_bbox) + [r1 - r0, rank], group)
+    assert rows.shape == (world, 6) and rows[:, 5].tolist() == list(range(world)) and int(rows[:, 4].sum()) == R
+    assert parallel.union_bbox(rows[:, :4]) == bbox
+    assert parallel.union_bbox(rows[:0, :4]) == (np.inf, -np.inf, np.inf, -np.inf)
     geom = LatticeGeom.anchored(s["spacing"], s["spacing"], s["xt"], s["yt"]).expanded(*g["lattice"])
     assert geom.strictly_contains(bbox)
     pf = O.Field(s["spacing"], s["spacing"], s["xt"], s["yt"])
@@ -78,6 +83,8 @@ def test_identity_without_group():
     from onekapy_b200 import parallel
     assert parallel.reduce_bbox((1.0, 2.0, 3.0, 4.0)) == (1.0, 2.0, 3.0, 4.0)
     assert parallel.sum_int(7) == 7 and parallel.any_rank(True) is True
+    assert parallel.gather_rows([1.0, 2.0]).tolist() == [[1.0, 2.0]]
+    assert parallel.union_bbox([[0, 1, 2, 3], [np.nan, 0, 0, 0], [-1, 0.5, 2.5, 9]]) == (-1.0, 1.0, 2.0, 9.0)
     assert parallel.init_from_env() == (0, 1, None) or os.environ.get("WORLD_SIZE", "1") != "1"
 
 
