@@ -194,7 +194,8 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
  * than tile/(sqrt(2) eta) from a tile's centre being "far".  Truncation <= eta^order/(1 - eta) relative to a far
  * term (3e-15 for eta = 0.3, order = 28); particles outside the grid, unconfined flow and models whose nw / xo / yo
  * differ from the ones given here use the direct sum.  The tables depend on the well COORDINATES only (host pointer;
- * must be the wells later passed as well_xy_dev); the realization-dependent coefficients are formed on the device
+ * must be the wells later passed as well_xy_dev: every launch checks that on the device, and oneka_read_stats fails
+ * with ONEKA_ERR_ARG when a launch since the last oneka_reset_stats was handed other coordinates); the realization-dependent coefficients are formed on the device
  * per launch.  order_fp64: only meaningful in builds with ONEKA_FF_TAIL=1, where the first order_fp64 terms are evaluated
  * in FP64 and the rest -- whose coefficients are below 2^-24 of the far field once eta^order_fp64 <= 2^-24 -- in FP32
  * (0 chooses that split); the shipped build evaluates every term in FP64 (the FP32 tail measured slower) and

@@ -71,9 +71,7 @@ struct oneka_ctx {
         unsigned short *near_cnt = nullptr;   // [ntiles]
         double2 *coef = nullptr;              // [realizations of a launch][ntiles][order], grow-only
         size_t coef_bytes = 0;
-        std::vector<double> wells;            // [nw][2] the coordinates the tables were built from (host copy)
-        const void *verified_ptr = nullptr;   // the last well_xy_dev whose contents were compared with `wells` ...
-        bool verified_same = false;           // ... and the outcome (prepare_farfield)
+        double *wells = nullptr;              // [nw][2] device copy of the coordinates the tables were built from (ff_check_wells_kernel)
         // unconfined flow (oneka_set_farfield_unconfined)
         bool unconfined = false;
         double *Lg = nullptr;                 // [ntiles][nw] ln |z_w - z_c| of the far wells
@@ -222,6 +220,22 @@ farfield_coef_unc_kernel(int nw, int ntiles, int order, const double2 *__restric
         for (int w = 0; w < nw; ++w) a = fma(qr[w] * 0.15915494309189535, Lg[(size_t)t * nw + w], a);
         b0[(size_t)r * ntiles + t] = a;
     }
+}
+
+// The far-field tables are geometry: they belong to the well coordinates oneka_set_farfield was given.  Every launch that
+// uses them compares the wells it was handed with that copy (bitwise; one CTA, in stream order, nothing on the host) and
+// counts a mismatch in the statistics block; oneka_read_stats then FAILS instead of returning numbers computed from near
+// terms of one well field and polynomials of another.
+__global__ void __launch_bounds__(128)
+ff_check_wells_kernel(int nw, const double *__restrict__ built_from, const double *__restrict__ well_xy, unsigned long long *stats)
+{
+    __shared__ unsigned int bad;
+    if (threadIdx.x == 0) bad = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * nw; i += blockDim.x)
+        if (__double_as_longlong(built_from[i]) != __double_as_longlong(well_xy[i])) bad = 1u;
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) atomicAdd(stats + STAT_FF_MISMATCH, 1ULL);
 }
 
 // register(1.0) for a batch of realizations (probabilityfield.py:357-359): one thread per bitmap word position,
@@ -571,18 +585,6 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     const oneka_ctx::FarField &f = ctx->ff;
     use = f.on && (m->confined || f.unconfined) && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
     if (!use) return ONEKA_OK;
-    // The tables were built from a HOST copy of the well coordinates (oneka_set_farfield).  A caller that hands over other
-    // wells with the same count and origin must not get near terms from the new coordinates and polynomials from the old
-    // ones: the first time a device pointer is seen its contents are compared with that copy (one small synchronous
-    // read per new pointer, nothing on later launches), and a mismatch means direct sums.
-    if (well_xy_dev != f.verified_ptr) {
-        std::vector<double> now((size_t)f.nw * 2);
-        CUDA_TRY(cudaMemcpyAsync(now.data(), well_xy_dev, now.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->ff.verified_ptr = well_xy_dev;
-        ctx->ff.verified_same = memcmp(now.data(), f.wells.data(), now.size() * sizeof(double)) == 0;
-    }
-    if (!f.verified_same) { use = false; return ONEKA_OK; }
     if (!m->confined && track_smem(f.nw) + (((size_t)f.ntx * f.nty * f.order * 24 + (size_t)f.ntx * f.nty * (10 + 2 * f.max_near) + 15) & ~(size_t)15) > 200 * 1024) {
         use = false;                                                  // the unconfined tables (c64 + p32) do not fit: direct sums
         return ONEKA_OK;
@@ -597,6 +599,7 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     }
     const long long nblk = nr * ntiles;
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many (realization, tile) pairs in one launch (%lld)", nblk);
+    ff_check_wells_kernel<<<1, 128, 0, ctx->stream>>>(f.nw, f.wells, well_xy_dev, ctx->stats_dev);
     if (m->confined) {
         farfield_coef_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, q, poro, thick, ctx->ff.coef);
     } else {
@@ -609,7 +612,7 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
         }
         farfield_coef_unc_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(f.nw, ntiles, f.order, f.P, f.Lg, q, ctx->ff.coef, ctx->ff.b0);
     }
-    ctx->launches++;
+    ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     out.ntx = f.ntx; out.nty = f.nty; out.n64 = f.n64; out.n32 = f.order - f.n64; out.max_near = f.max_near;
     out.gx0 = f.gx0; out.gy0 = f.gy0; out.inv_tile = 1.0 / f.tile;
@@ -772,6 +775,7 @@ void oneka_destroy(oneka_ctx *ctx)
     if (ctx->ff.near_idx) cudaFree(ctx->ff.near_idx);
     if (ctx->ff.near_raw) cudaFree(ctx->ff.near_raw);
     if (ctx->ff.b0) cudaFree(ctx->ff.b0);
+    if (ctx->ff.wells) cudaFree(ctx->ff.wells);
     if (ctx->comm && ctx->comm_owned) { if (const nccl_api *N = nccl()) N->CommDestroy(ctx->comm); }
     delete ctx;
 }
@@ -843,7 +847,7 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (f.Lg) { cudaFree(f.Lg); f.Lg = nullptr; }
     if (f.near_idx) { cudaFree(f.near_idx); f.near_idx = nullptr; }
     if (f.near_raw) { cudaFree(f.near_raw); f.near_raw = nullptr; }
-    f.wells.clear(); f.verified_ptr = nullptr; f.verified_same = false;
+    if (f.wells) { cudaFree(f.wells); f.wells = nullptr; }
     if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
     FFTables T;
     if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
@@ -866,7 +870,8 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     CUDA_TRY(cudaMemcpy(f.Lg, T.Lg.data(), T.Lg.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_idx, T.idx.data(), T.idx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(f.near_raw, T.cnt_raw.data(), T.cnt_raw.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    f.wells.assign(well_xy_host, well_xy_host + (size_t)nw * 2);
+    CUDA_TRY(cudaMalloc(&f.wells, (size_t)nw * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(f.wells, well_xy_host, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice));
     f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.n64 = n64; f.max_near = T.max_near;
     f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
     f.on = true;
@@ -947,6 +952,10 @@ int oneka_read_stats(oneka_ctx *ctx, oneka_stats *out)
     unsigned long long h[N_STATS];
     CUDA_TRY(cudaMemcpyAsync(h, ctx->stats_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h[STAT_FF_MISMATCH])
+        return fail(ONEKA_ERR_ARG, "%llu launch(es) since the last oneka_reset_stats used far-field tables built for OTHER well coordinates than "
+                                   "the well_xy_dev they were given: call oneka_set_farfield again (or switch it off) when the wells change; "
+                                   "the results of those launches are invalid", (unsigned long long)h[STAT_FF_MISMATCH]);
     out->attempts = h[STAT_ATTEMPTS]; out->steps = h[STAT_STEPS]; out->paths = h[STAT_PATHS];
     out->n_not_ok = h[STAT_NOT_OK]; out->n_clipped = h[STAT_CLIPPED]; out->exact_tests = h[STAT_EXACT];
     if (h[STAT_PATHS] == 0) {

@@ -107,7 +107,7 @@ struct TrackParams {
 };
 
 enum : int { STAT_ATTEMPTS = 0, STAT_STEPS = 1, STAT_PATHS = 2, STAT_NOT_OK = 3, STAT_CLIPPED = 4, STAT_EXACT = 5,
-             STAT_XMIN = 6, STAT_XMAX = 7, STAT_YMIN = 8, STAT_YMAX = 9, STAT_WORDS = 10 };
+             STAT_XMIN = 6, STAT_XMAX = 7, STAT_YMIN = 8, STAT_YMAX = 9, STAT_FF_MISMATCH = 10, STAT_WORDS = 11 };
 
 struct LatticeDev {
     double xmin, ymin, dx, dy;

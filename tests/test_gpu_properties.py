@@ -121,7 +121,7 @@ def test_batching_independent_of_workspace(eng):
     n0 = small.launch_count()
     small.capture(spec, dp2, geom, b)
     small.synchronize()
-    per_batch = 2 + (1 if small.farfield_info() else 0)        # track + flush (+ the far-field coefficient kernel)
+    per_batch = 2 + (2 if small.farfield_info() else 0)        # track + flush (+ the far-field coefficient kernel and the well check)
     assert small.launch_count() - n0 == per_batch * 14
     assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
     small.close()

@@ -93,38 +93,39 @@ def test_compute_capturezone_on_unanchored_field(eng, golden):
 
 
 def test_farfield_tables_are_bound_to_their_wells(eng, golden):
-    """oneka_set_farfield builds its tables from a host copy of the wells; a caller that then passes OTHER coordinates with
-    the same count and origin must get the direct sums of the new wells, not near terms from the new and
-    polynomials from the old ones."""
+    """oneka_set_farfield builds its tables from the wells it is given; a C-ABI caller that then passes OTHER coordinates
+    with the same count and origin would get near terms from the new wells and polynomials from the old ones.
+    Every launch compares the wells on the device and oneka_read_stats refuses to report such a run."""
     import copy
-    import torch
     g = golden("sto_perham.npz")
     s, spec, par = spec_of(g)
     gm = fixed_geom(g, s)
+    eng.farfield = "auto"
+    eng.reset_stats()
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    assert eng.farfield_info() is not None and eng.read_stats()["n_not_ok"] == 0
     moved = copy.copy(spec)
     moved.well_xy = spec.well_xy.copy()
     moved.well_xy[1:] += 35.0                                     # every well but the target (the origin stays)
-    # reference result for the moved wells: direct sums
-    eng.farfield = "off"
-    want = eng.new_counts(gm)
-    eng.reset_stats()
-    eng.capture(moved, eng.upload(moved, par), gm, want)
-    st_want = eng.read_stats()
-    # tables for the ORIGINAL wells, then a raw C-ABI call with the moved ones (Engine itself would rebuild them)
-    eng.farfield = "auto"
-    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
-    assert eng.farfield_info() is not None
     from onekapy_b200 import _cabi
     dp = eng.upload(moved, par)
     got = eng.new_counts(gm)
     m, lat = moved.model_desc(), gm.as_lattice(moved.umbra)
-    eng.reset_stats()
+    eng.reset_stats()                                             # a raw C-ABI call (Engine itself would rebuild the tables)
     _cabi.check(eng._L.oneka_capture(eng._h, C.byref(m), C.byref(lat), dp.well_xy.data_ptr(), len(par), s["P"], dp.q.data_ptr(),
                                      dp.cond.data_ptr(), dp.poro.data_ptr(), dp.thick.data_ptr(), dp.coef.data_ptr(),
                                      dp.start_xy.data_ptr(), got.data_ptr(), None, None, None))
-    st_got = eng.read_stats()
-    assert st_got["attempts"] == st_want["attempts"] and st_got["steps"] == st_want["steps"]
-    assert torch.equal(got, want)
+    with pytest.raises(_cabi.OnekaError, match="OTHER well coordinates"):
+        eng.read_stats()
+    eng.reset_stats()
+    # through Engine the tables follow the wells: same call, correct result (== direct sums of the moved wells)
+    eng.capture(moved, dp, gm, eng.new_counts(gm))
+    st = eng.read_stats()
+    eng.farfield = "off"
+    eng.reset_stats()
+    eng.capture(moved, dp, gm, eng.new_counts(gm))
+    assert eng.read_stats()["attempts"] == st["attempts"]
+    eng.farfield = "auto"
 
 
 def test_own_communicator_single_rank(eng):
