@@ -153,6 +153,7 @@ class Engine:
         self._h = _cabi.create(self.index)
         self._geom_hint = collections.OrderedDict()     # problem key -> (work lattice, far-field box); small LRU
         self._comm = None                               # (world, rank) once oneka_comm_init_rank has run (init_comm)
+        self.last_stats = None                          # statistics of the last run() / run_exact() (the drop-in drivers return only the field)
         # far-field compression of the well sum (oneka_set_farfield): "auto" = wherever it pays, "off" = direct sums only,
         # "force" = wherever it applies, whatever the cost model says (tests, A/B runs)
         self.farfield = "off" if os.environ.get("ONEKA_FARFIELD", "auto").lower() in ("0", "off", "no") else "auto"
@@ -558,7 +559,7 @@ class Engine:
         (oneka_path_bboxes, then oneka_capture_clipped for everything) is cheaper; it is also what compute_capturezone uses.
         `base`: the grid before the first path (default: fresh 3 x 3 on the target, stochastic.py:212)."""
         from . import parallel
-        from .lattice import clip_windows, affected_paths
+        from .lattice import clip_windows, clip_windows_rows, realization_boxes, union_before, affected_realizations
         torch = self.torch
         R, P = len(params), int(spec.npaths)
         start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
@@ -601,8 +602,10 @@ class Engine:
             out = _to_host(counts).view(np.uint32)
             if per_path and pp is not None:
                 pp = {k: _to_host(v) for k, v in pp.items()}
+            self.last_stats = stats
             return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=final)
 
+        tick = _PhaseTimer(self.torch, self.device)
         # ---- 1. lattice estimate ----
         self.reset_stats()
         if hint is None:
@@ -627,6 +630,7 @@ class Engine:
             work = work.expanded(base.xmin + 0.5 * base.deltax, base.xmax - 0.5 * base.deltax,
                                  base.ymin + 0.5 * base.deltay, base.ymax - 0.5 * base.deltay)      # the base grid is part of the result
 
+        tick('pilot')
         # ---- 2. ONE fused pass: count grid + per-path boxes; realizations that leave `work` are flagged, not registered ----
         counts = self.new_counts(work)
         flags = torch.zeros(R, dtype=torch.int32, device=self.device)
@@ -635,6 +639,7 @@ class Engine:
         pp = self.capture(spec, dp, work, counts, per_path=per_path, flags=flags, ff_box=ff_box, bbox_out=bb) if R else None
         stats = self.read_stats()
 
+        tick('fused_pass')
         # ---- 3. the grid each path met ----
         allb = parallel.gather_rows(stats["bbox"], group, dev)
         prior = parallel.union_bbox(allb[:rank]) if rank else None
@@ -644,30 +649,47 @@ class Engine:
         final = base.expanded(*true_bbox)
         nflag = naff = 0
         if R:
-            clip = clip_windows(torch, base, final, bb, prior)
-            aff_path = affected_paths(torch, final, bb, clip, spec.umbra)
-            aff = aff_path.any(dim=1) | (flags != 0)
+            # everything below is per REALIZATION (R boxes, one scan over R) except for the affected realizations themselves,
+            # whose paths get their individual windows: nothing of size R x P but four reductions over the boxes
+            rb = realization_boxes(torch, bb)
+            before = union_before(torch, rb, prior)
+            aff = affected_realizations(torch, base, final, rb, before, spec.umbra) | (flags != 0)
             redo = aff.nonzero().reshape(-1)                       # affected realizations, in order
             undo = (aff & (flags == 0)).nonzero().reshape(-1)      # ... of which these were registered in pass 2
             nflag, naff = int((flags != 0).sum().item()), int(redo.numel())
-            del bb, aff_path
+            clip = clip_windows_rows(torch, base, final, bb.index_select(0, redo), before.index_select(0, redo)) if naff else None
+            del bb, rb
         stats["rerun_realizations"] = nflag
         stats["affected_realizations"] = naff
 
+        tick('windows')
         # ---- 4. fix-up ----
-        if R and int(undo.numel()):
-            minus = self.new_counts(work)
-            self.capture(spec, dp.select(undo), work, minus, ff_box=ff_box)
-            counts -= minus
-            del minus
         out_grid = self.new_counts(final)
-        _copy_overlap(counts, work, out_grid, final)
-        del counts
-        if R and naff:
-            self.capture(spec, dp.select(redo), final, out_grid, clip=clip.index_select(0, redo).contiguous(), ff_box=ff_box)
+        if R and 2 * naff > R:
+            # most realizations are affected (e.g. a capture zone whose downstream edge is the start ring itself: the
+            # reference's grid never reaches an umbra beyond it): one clipped pass over everything is cheaper than
+            # taking them out and putting them back
+            del counts
+            self.capture(spec, dp.select(redo), final, out_grid, clip=clip, ff_box=ff_box)
+            if naff < R:                                         # the few unaffected ones: unclipped is exact for them
+                keep = (~aff).nonzero().reshape(-1)
+                self.capture(spec, dp.select(keep), final, out_grid, ff_box=ff_box)
+        else:
+            if R and int(undo.numel()):
+                minus = self.new_counts(work)
+                self.capture(spec, dp.select(undo), work, minus, ff_box=ff_box)
+                counts -= minus
+                del minus
+            _copy_overlap(counts, work, out_grid, final)
+            del counts
+            if R and naff:
+                self.capture(spec, dp.select(redo), final, out_grid, clip=clip, ff_box=ff_box)
+        tick('fixup')
         if group is not None:
             self.allreduce_counts(out_grid, group)
         out = _to_host(out_grid).view(np.uint32)
+        tick('allreduce_d2h')
+        stats["phases_ms"] = tick.result()
         if per_path and pp is not None:
             pp = {k: _to_host(v) for k, v in pp.items()}
         if reuse_lattice:
@@ -675,6 +697,7 @@ class Engine:
             pw, ph = margin * max(tb[1] - tb[0], spec.umbra), margin * max(tb[3] - tb[2], spec.umbra)
             keep = work if nflag == 0 else work.expanded(tb[0] - pw, tb[1] + pw, tb[2] - ph, tb[3] + ph)
             self._hint_put(key, (keep, ff_box))
+        self.last_stats = stats
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=work)
 
     # -- lattice hints: a small LRU keyed by the problem (bounded, and replaced when it proved too small) ----
@@ -827,7 +850,31 @@ class Engine:
                 tb = true_bbox
                 pw, ph = margin * max(tb[1] - tb[0], spec.umbra), margin * max(tb[3] - tb[2], spec.umbra)
                 self._hint_put(key, (work_geom.expanded(tb[0] - pw, tb[1] + pw, tb[2] - ph, tb[3] + ph), ff_box))
+        self.last_stats = stats
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=geom)
+
+
+class _PhaseTimer:
+    """Wall clock per phase of a run (ONEKA_PHASES=1: synchronises the device at every tick; otherwise free and empty)."""
+
+    def __init__(self, torch, device):
+        self.on = os.environ.get("ONEKA_PHASES", "0") == "1"
+        self.torch, self.device, self.t, self.out = torch, device, None, {}
+        if self.on:
+            import time
+            self.clock = time.perf_counter
+            torch.cuda.synchronize(device)
+            self.t = self.clock()
+
+    def __call__(self, name):
+        if self.on:
+            self.torch.cuda.synchronize(self.device)
+            now = self.clock()
+            self.out[name] = self.out.get(name, 0.0) + 1e3 * (now - self.t)
+            self.t = now
+
+    def result(self):
+        return dict(self.out) if self.on else None
 
 
 def farfield_grid(box, max_tiles=64, min_tile=100.0):

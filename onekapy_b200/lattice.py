@@ -114,9 +114,16 @@ def clip_windows(torch, base, final, bb, prior=None):
         hi_x = torch.clamp(hi_x, min=float(prior[1]))
         lo_y = torch.clamp(lo_y, max=float(prior[2]))
         hi_y = torch.clamp(hi_y, min=float(prior[3]))
+    left, right, bottom, top = _grid_windows(torch, base, final, lo_x, hi_x, lo_y, hi_y)
+    return torch.stack([left, right, bottom, top], dim=1).to(torch.int32).reshape(R, P, 4).contiguous()
+
+
+def _grid_windows(torch, base, final, lo_x, hi_x, lo_y, hi_y):
+    """Index ranges (in `final`) of the reference's grid after expand() to the box (lo_x, hi_x, lo_y, hi_y) [tensors of one
+    shape; +-inf = nothing inserted yet = the base grid]: left, right, bottom, top (half-open) as float64 tensors."""
     i0, j0 = final.offset_of(base)                       # where the base grid sits inside the final lattice
 
-    def cells_below(g0, c, d):                            # expansions so that g0 - k d < c
+    def cells_below(g0, c, d):                            # expansions so that g0 - k d < c   (probabilityfield.py:229-245)
         return torch.where(c <= g0, torch.floor((g0 - c) / d) + 1.0, torch.zeros_like(c))
 
     def cells_above(g1, c, d):                            # expansions so that g1 + k d > c
@@ -126,23 +133,62 @@ def clip_windows(torch, base, final, bb, prior=None):
     right = j0 + base.ncols + cells_above(base.xmax, hi_x, base.deltax)
     bottom = i0 - cells_below(base.ymin, lo_y, base.deltay)
     top = i0 + base.nrows + cells_above(base.ymax, hi_y, base.deltay)
-    return torch.stack([left, right, bottom, top], dim=1).to(torch.int32).reshape(R, P, 4).contiguous()
+    return left, right, bottom, top
 
 
-def affected_paths(torch, final, bb, clip, umbra):
-    """bool [R, P]: could the reference's grid-at-that-moment have clipped ANY segment window of the path?
+def realization_boxes(torch, bb):
+    """[R, P, 4] per-path boxes -> [R, 4] per-realization boxes (min x, max x, min y, max y)."""
+    return torch.stack([bb[..., 0].amin(dim=1), bb[..., 1].amax(dim=1), bb[..., 2].amin(dim=1), bb[..., 3].amax(dim=1)], dim=1)
+
+
+def union_before(torch, rb, prior=None):
+    """[R, 4]: the union of the boxes of realizations 0..r-1 (and of `prior`, the box of everything other ranks inserted
+    earlier) -- what the reference's grid had been expanded to when realization r began; +-inf where nothing precedes."""
+    import math
+    R = int(rb.shape[0])
+    inf = float("inf")
+    first = [inf, -inf, inf, -inf]
+    if prior is not None and all(math.isfinite(v) for v in prior):
+        first = [float(v) for v in prior]
+    out = torch.empty_like(rb)
+    out[0] = torch.tensor(first, dtype=rb.dtype, device=rb.device)
+    if R > 1:
+        out[1:, 0] = torch.clamp(torch.cummin(rb[:-1, 0], 0).values, max=first[0])
+        out[1:, 1] = torch.clamp(torch.cummax(rb[:-1, 1], 0).values, min=first[1])
+        out[1:, 2] = torch.clamp(torch.cummin(rb[:-1, 2], 0).values, max=first[2])
+        out[1:, 3] = torch.clamp(torch.cummax(rb[:-1, 3], 0).values, min=first[3])
+    return out
+
+
+def affected_realizations(torch, base, final, rb, before, umbra):
+    """bool [R]: could the reference's grid-at-that-moment have clipped ANY segment window of realization r?
 
     insert() needs, for a segment, the nodes floor((min - umbra - xmin)/delta) .. floor((max + umbra - xmin)/delta)
-    (probabilityfield.py:298-301); every segment of a path lies inside the path's bounding box, so its windows lie
-    inside the box's window.  A path whose box window, widened by ONE MORE cell on every side (the floors here are not
-    the reference's operation-for-operation floors), sits inside its clip window was rasterised exactly as the
-    reference did even without the clip.  Conservative by construction: a path wrongly called affected only costs time.
-    bb: float64 [R, P, 4] (min x, max x, min y, max y); clip: int32 [R, P, 4] from clip_windows (indices of `final`)."""
+    (probabilityfield.py:298-301).  Every segment of realization r lies inside its box rb[r], and every grid the
+    realization's paths met contains the grid as expanded to `before[r]` (the grid only grows).  So a realization whose box
+    window, widened by ONE MORE cell on every side (the floors here are not the reference's operation-for-operation
+    floors), sits inside that grid was rasterised exactly as the reference did even without any clip.  Conservative by
+    construction: a realization wrongly called affected only costs time."""
     u = float(umbra)
-    c = clip.to(torch.float64)
-    need_l = torch.floor((bb[..., 0] - u - final.xmin) / final.deltax) - 1.0
-    need_r = torch.floor((bb[..., 1] + u - final.xmin) / final.deltax) + 2.0        # half-open upper end + one cell
-    need_b = torch.floor((bb[..., 2] - u - final.ymin) / final.deltay) - 1.0
-    need_t = torch.floor((bb[..., 3] + u - final.ymin) / final.deltay) + 2.0
-    inside = (need_l >= c[..., 0]) & (need_r <= c[..., 1]) & (need_b >= c[..., 2]) & (need_t <= c[..., 3])
+    left, right, bottom, top = _grid_windows(torch, base, final, before[:, 0], before[:, 1], before[:, 2], before[:, 3])
+    need_l = torch.floor((rb[:, 0] - u - final.xmin) / final.deltax) - 1.0
+    need_r = torch.floor((rb[:, 1] + u - final.xmin) / final.deltax) + 2.0        # half-open upper end + one cell
+    need_b = torch.floor((rb[:, 2] - u - final.ymin) / final.deltay) - 1.0
+    need_t = torch.floor((rb[:, 3] + u - final.ymin) / final.deltay) + 2.0
+    inside = (need_l >= left) & (need_r <= right) & (need_b >= bottom) & (need_t <= top)
     return ~inside                                               # (a nan box compares false everywhere -> affected)
+
+
+def clip_windows_rows(torch, base, final, bb, before):
+    """Per-path raster windows for SELECTED realizations: bb [n, P, 4] their per-path boxes, before [n, 4] the union of
+    everything inserted before each of them (union_before).  Path p of such a realization met the grid as expanded to
+    before U boxes of its paths 0..p.  Returns int32 [n, P, 4] = left, right, bottom, top (half-open, indices of `final`)."""
+    n, P = int(bb.shape[0]), int(bb.shape[1])
+    if n * P == 0:
+        return torch.zeros((n, P, 4), dtype=torch.int32, device=bb.device)
+    lo_x = torch.minimum(torch.cummin(bb[..., 0], 1).values, before[:, None, 0])
+    hi_x = torch.maximum(torch.cummax(bb[..., 1], 1).values, before[:, None, 1])
+    lo_y = torch.minimum(torch.cummin(bb[..., 2], 1).values, before[:, None, 2])
+    hi_y = torch.maximum(torch.cummax(bb[..., 3], 1).values, before[:, None, 3])
+    w = _grid_windows(torch, base, final, lo_x, hi_x, lo_y, hi_y)
+    return torch.stack(w, dim=2).to(torch.int32).contiguous()

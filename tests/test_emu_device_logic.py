@@ -244,7 +244,7 @@ def test_one_pass_exact_clip_pipeline(golden, name, shards):
     auto-expanding grid, cell for cell; with 2 shards, shard 1's paths come after shard 0's (its windows start from
     shard 0's box) and the grids are summed -- what the allreduce does across GPUs."""
     import torch
-    from onekapy_b200.lattice import clip_windows, affected_paths
+    from onekapy_b200.lattice import clip_windows, clip_windows_rows, realization_boxes, union_before, affected_realizations
     g = golden(name)
     s, spec, par = spec_of(g)
     ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
@@ -273,10 +273,15 @@ def test_one_pass_exact_clip_pipeline(golden, name, shards):
             pb = boxes[:k]
             prior = (min(b[0] for b in pb), max(b[1] for b in pb), min(b[2] for b in pb), max(b[3] for b in pb))
         bb = torch.from_numpy(passA[k]["path_bbox"])
-        clip = clip_windows(torch, base, final, bb, prior)
-        aff = affected_paths(torch, final, bb, clip, s["umbra"]).any(dim=1).numpy()
+        rb = realization_boxes(torch, bb)
+        before = union_before(torch, rb, prior)
+        aff = affected_realizations(torch, base, final, rb, before, s["umbra"]).numpy()
         idx = np.nonzero(aff)[0]
         naff += len(idx)
+        sel = torch.from_numpy(idx)
+        clip = clip_windows_rows(torch, base, final, bb.index_select(0, sel), before.index_select(0, sel))
+        # the per-realization form gives the affected realizations the windows the flat running union gives every path
+        assert torch.equal(clip, clip_windows(torch, base, final, bb, prior).index_select(0, sel))
         counts = passA[k]["counts"].astype(np.int64)
         if len(idx):
             sub = RealizationParams(q=par.q[r0:r1][idx], cond=par.cond[r0:r1][idx], poro=par.poro[r0:r1][idx],
@@ -287,29 +292,36 @@ def test_one_pass_exact_clip_pipeline(golden, name, shards):
         assert counts.sum() == counts[i0:i0 + final.nrows, j0:j0 + final.ncols].sum()      # nothing is left outside the final extents
         total += counts[i0:i0 + final.nrows, j0:j0 + final.ncols]
         if len(idx):
-            total += emu.capture(spec, sub, ring, 1, geom=final, clip=clip.numpy()[idx])["counts"]
+            total += emu.capture(spec, sub, ring, 1, geom=final, clip=clip.numpy())["counts"]
     want = g["auto_counts"].astype(np.int64)
     assert total.shape == want.shape and np.count_nonzero(total != want) == 0
     assert naff >= 1                                             # the very first paths always meet a grid still growing
 
 
-def test_affected_paths_is_conservative_and_selective():
-    """lattice.affected_paths on synthetic boxes: a path deep inside its window is not affected, one within umbra + a cell
-    of the window's edge is; nan boxes count as affected."""
+def test_affected_realizations_is_conservative_and_selective():
+    """lattice.affected_realizations on synthetic boxes: a realization deep inside the grid that preceded it is not affected,
+    one within umbra + a cell of that grid's edge is; the first realization (nothing before it: the 3 x 3 base grid) and nan
+    boxes always are."""
     import torch
-    from onekapy_b200.lattice import affected_paths
-    final = LatticeGeom.anchored(4.0, 4.0, 0.0, 0.0).expanded(-400.0, 400.0, -400.0, 400.0)
-    i0 = int(round((0.0 - final.ymin) / 4.0))
-    j0 = int(round((0.0 - final.xmin) / 4.0))
-    win = [j0 - 50, j0 + 51, i0 - 50, i0 + 51]                    # nodes -200 .. 200 in both directions
-    bb = torch.tensor([[[-150.0, 150.0, -150.0, 150.0],           # inside with 50 m to spare
-                        [-190.0, 150.0, -150.0, 150.0],           # 10 m from the left edge: umbra 8 + 4 m of cell -> affected
-                        [-150.0, 150.0, -150.0, 192.5],           # top: node 50 is needed (192.5 + 8 > 200), + a cell of slack > window 
-                        [-150.0, 150.0, -150.0, 180.0],           # top: 20 m to spare -> fine
-                        [float("nan"), 1.0, 0.0, 1.0]]], dtype=torch.float64)
-    clip = torch.tensor([[win] * 5], dtype=torch.int32)
-    got = affected_paths(torch, final, bb, clip, 8.0)[0].tolist()
-    assert got == [False, True, True, False, True]
+    from onekapy_b200.lattice import union_before, affected_realizations
+    base = LatticeGeom.anchored(4.0, 4.0, 0.0, 0.0)
+    final = base.expanded(-400.0, 400.0, -400.0, 400.0)
+    rb = torch.tensor([[-199.0, 199.0, -199.0, 199.0],           # 0: the first one (base grid only)          -> affected
+                       [-150.0, 150.0, -150.0, 150.0],           # 1: grid now spans -200 .. 200, 50 m to spare -> fine
+                       [-190.0, 150.0, -150.0, 150.0],           # 2: 10 m from the left edge: umbra 8 + a cell  -> affected
+                       [-150.0, 150.0, -150.0, 192.5],           # 3: top: node 50 is needed (192.5 + 8 > 200)   -> affected
+                       [-150.0, 150.0, -150.0, 180.0],           # 4: top: 20 m to spare                         -> fine
+                       [-150.0, 300.0, -150.0, 150.0],           # 5: extends the union to the right             -> affected
+                       [-150.0, 280.0, -150.0, 150.0],           # 6: inside what 5 left behind                  -> fine
+                       [float("nan"), 1.0, 0.0, 1.0]], dtype=torch.float64)
+    before = union_before(torch, rb)
+    assert before[0].tolist() == [float("inf"), -float("inf"), float("inf"), -float("inf")]
+    assert before[1].tolist() == [-199.0, 199.0, -199.0, 199.0] and before[6].tolist() == [-199.0, 300.0, -199.0, 199.0]
+    got = affected_realizations(torch, base, final, rb, before, 8.0).tolist()
+    assert got == [True, False, True, True, False, True, False, True]
+    # other ranks' shards come first
+    b2 = union_before(torch, rb, prior=(-250.0, 100.0, -100.0, 100.0))
+    assert b2[0].tolist() == [-250.0, 100.0, -100.0, 100.0] and b2[1].tolist() == [-250.0, 199.0, -199.0, 199.0]
 
 
 def test_unconfined_far_field_vs_direct_and_oracle():
