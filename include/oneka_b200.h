@@ -196,15 +196,19 @@ int oneka_capture_clipped(oneka_ctx *ctx, const oneka_model_desc *m, const oneka
  * differ from the ones given here use the direct sum.  The tables depend on the well COORDINATES only (host pointer;
  * must be the wells later passed as well_xy_dev: every launch checks that on the device, and oneka_read_stats fails
  * with ONEKA_ERR_ARG when a launch since the last oneka_reset_stats was handed other coordinates); the realization-dependent coefficients are formed on the device
- * per launch.  order_fp64: only meaningful in builds with ONEKA_FF_TAIL=1, where the first order_fp64 terms are evaluated
- * in FP64 and the rest -- whose coefficients are below 2^-24 of the far field once eta^order_fp64 <= 2^-24 -- in FP32
- * (0 chooses that split); the shipped build evaluates every term in FP64 (the FP32 tail measured slower) and
- * ignores it.  nw = 0 or order = 0 switches the far field off (the default).  Synchronous.
+ * per launch.  order must be even; order 16 runs an unrolled evaluation (Engine's default: eta = 0.15, order 16, truncation
+ * 8e-14 of a far term -- below the 1e-12 of the Newton reciprocal in the direct sum).  order_fp64 is ignored (the slot of
+ * an FP32 tail that measured slower and was removed).  nw = 0 or order = 0 switches the far field off (the default).  Synchronous.
  * max_near_out / mean_near_out (may be NULL): padded length of the longest near list, mean near wells per tile.   */
 int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, double xo, double yo,
                        double x0, double y0, double tile, int32_t ntx, int32_t nty, int32_t order, double eta,
                        int32_t order_fp64, int32_t *max_near_out, double *mean_near_out);
-/* Opt-in (default off; arithmetic validated on the host emulation, not yet timed on hardware): also use the far field for
+/* What the tables of the last oneka_set_farfield need: tiles, order, longest near list, dynamic shared memory per CTA of the
+ * confined / unconfined tracking kernels, and the budget per CTA that keeps two of those CTAs on an SM (beyond it the kernel
+ * still runs, at half the occupancy: Engine sizes the tile grid to stay inside).  Any pointer may be NULL.               */
+int oneka_farfield_info(oneka_ctx *ctx, int32_t *ntiles, int32_t *order, int32_t *max_near, uint64_t *smem_confined,
+                        uint64_t *smem_unconfined, uint64_t *smem_budget);
+/* Also use the far field for
  * UNCONFINED flow (Model.compute_velocity, oneka/model.py:353-389).  The far wells' part of the potential -- needed only to
  * decide whether the aquifer is fully saturated at the point -- comes from the same coefficients in FP32; where that decision
  * is not certain the evaluation falls back to the direct sums with FP64 logs, exactly as without the far field.            */

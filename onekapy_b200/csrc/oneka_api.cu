@@ -37,21 +37,25 @@ static int fail(int code, const char *fmt, ...)
             return fail(ONEKA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-#ifndef ONEKA_TRACK_THREADS
-#define ONEKA_TRACK_THREADS 128
+// CTA shapes of the tracking kernel (every warp stays inside one realization; P = 1000 paths = 8 x 125 = 4 x 250 lanes).
+//   direct sums (and everything without the far field): 128 threads, 6 CTAs per SM -- 80 registers, 24 warps: these kernels are
+//     bound by the issue port and want the warps (measured 5 / 6 / 8 CTAs within 2 %; 256 x 2 loses 6 %, profiles/r02_knob_scan5.txt);
+//   far field: 256 threads, 2 CTAs per SM -- 128 registers (no spills; 80 cost 200 B of them) and up to ~112 KB of shared memory
+//     for the realization's coefficient table, i.e. ~6x the tiles of the 128 x 6 shape at a lower order: C3 79.9 -> 64.6 ms,
+//     C4 33.1 -> 25.6 ms per step (profiles/r02_knob_scan2-4.txt).
+constexpr int TRACK_THREADS = 128, TRACK_MIN_CTAS = 6;
+constexpr int FF_THREADS = 256, FF_MIN_CTAS = 2;
+#ifndef ONEKA_FF_UNC_THREADS                 // unconfined far field: same shape (A/B knob while it is being measured)
+#define ONEKA_FF_UNC_THREADS 256
 #endif
-constexpr int TRACK_THREADS = ONEKA_TRACK_THREADS;   // warps per CTA x 32; every warp stays inside one realization
-#ifndef TRACK_MIN_CTAS
-#define TRACK_MIN_CTAS (768 / ONEKA_TRACK_THREADS)   // tracking only: <= 80 registers/thread -> 24 warps per SM
-#endif
-#ifndef FUSED_MIN_CTAS
-#define FUSED_MIN_CTAS (768 / ONEKA_TRACK_THREADS)                    // + rasteriser: 80 registers too (260 B of spills, all on the cold exact/fallback
-#endif                                      // paths); measured 6.19e9 attempts/s vs 5.92e9 at 4 CTAs/120 regs, 5.74e9 at 5/96
+constexpr int FF_UNC_THREADS = ONEKA_FF_UNC_THREADS, FF_UNC_MIN_CTAS = 768 / ONEKA_FF_UNC_THREADS == 3 ? 2 : 768 / ONEKA_FF_UNC_THREADS;
+constexpr int FF_ORDER_UNROLLED = 16;        // the order whose Horner loop is unrolled at compile time (Engine's default)
 constexpr int N_STATS = 16;
 
 struct oneka_ctx {
     int device = 0;
     int sm_count = 0;
+    size_t smem_per_sm = 0;                 // cudaDevAttrMaxSharedMemoryPerMultiprocessor
     cudaStream_t stream = nullptr;
     unsigned int *bitmaps = nullptr;        // registration bitmaps, all-zero between calls
     size_t bitmap_bytes = 0;
@@ -64,8 +68,9 @@ struct oneka_ctx {
     // far-field compression (oneka_set_farfield): tile geometry, static tables, per-launch coefficient workspace
     struct FarField {
         bool on = false;
-        int nw = 0, ntx = 0, nty = 0, order = 0, n64 = 0, max_near = 0;
+        int nw = 0, ntx = 0, nty = 0, order = 0, max_near = 0;
         double xo = 0, yo = 0, gx0 = 0, gy0 = 0, tile = 0, eta = 0, mean_near = 0;
+        size_t smem_confined = 0, smem_unconfined = 0;   // dynamic shared memory per CTA with these tables
         double2 *P = nullptr;                 // [ntiles][nw][order]
         unsigned int *near_off = nullptr;     // [ntiles][max_near] byte offsets into the well store
         unsigned short *near_cnt = nullptr;   // [ntiles]
@@ -96,11 +101,11 @@ struct oneka_ctx {
 // ------------------------------------------------------------------------------------------
 // stage_realization<CONFINED> (the per-CTA well store and realization constants) lives in oneka_device.cuh
 
-// One CTA = 128 consecutive paths of ONE realization; grid = R * ceil(P/128).
-// FF (confined only): the realization's far-field coefficient table and the tiles' near lists are staged behind the
-// well store (see "Far-field compression" in oneka_device.cuh).
-template <bool CONFINED, int MODE, bool FF>
-__global__ void __launch_bounds__(TRACK_THREADS, MODE == 1 ? FUSED_MIN_CTAS : TRACK_MIN_CTAS)
+// One CTA = THREADS consecutive paths of ONE realization; grid = R * ceil(P/THREADS).
+// FF: the realization's far-field coefficient table and the tiles' near lists are staged behind the well store (see
+// "Far-field compression" in oneka_device.cuh); ORD = its order when that is a compile-time constant, else 0.
+template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff)
 {
     extern __shared__ double2 s_dyn[];
@@ -109,42 +114,28 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
     double *s_wells = reinterpret_cast<double *>(s_dyn);
     if (MODE == 1) stage_lattice(L, s_lat);
 
-    const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
+    const int chunks = (tp.P + THREADS - 1) / THREADS;
     const long long r = blockIdx.x / chunks;
-    const int p = (int)(blockIdx.x % chunks) * TRACK_THREADS + threadIdx.x;
-    FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
+    const int p = (int)(blockIdx.x % chunks) * THREADS + threadIdx.x;
+    FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (FF && CONFINED) {
-#if ONEKA_FF_COEF_GLOBAL
-        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
-        const double2 *s_c64 = ff.coef + (size_t)r * ntiles * order;             // read in place through L1 (all-FP64 builds only)
-        float2 *s_c32 = nullptr;
-        unsigned int *s_off = reinterpret_cast<unsigned int *>(s_dyn + ff_store_double2(tp.nw));
-        unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
-#else
-        const int ntiles = ff.ntx * ff.nty, order = ff.n64 + ff.n32;
+        const int ntiles = ff.ntx * ff.nty, order = ff.order;
         double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
-        float2 *s_c32 = reinterpret_cast<float2 *>(s_c64 + ntiles * ff.n64);
-        unsigned int *s_off = reinterpret_cast<unsigned int *>(s_c32 + ntiles * ff.n32);
+        unsigned int *s_off = reinterpret_cast<unsigned int *>(s_c64 + ntiles * order);
         unsigned short *s_cnt = reinterpret_cast<unsigned short *>(s_off + ntiles * ff.max_near);
         const double2 *g = ff.coef + (size_t)r * ntiles * order;
-        for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) {          // coalesced read of the realization's table
-            const int t = i / order, k = i - t * order;
-            const double2 c = g[i];
-            if (k < ff.n64) s_c64[t * ff.n64 + k] = c;
-            else s_c32[t * ff.n32 + (k - ff.n64)] = make_float2((float)c.x, (float)c.y);
-        }
-#endif
+        for (int i = threadIdx.x; i < ntiles * order; i += blockDim.x) s_c64[i] = g[i];     // coalesced copy of the realization's table
         for (int i = threadIdx.x; i < ntiles * ff.max_near; i += blockDim.x) s_off[i] = ff.near_off[i];
         for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = ff.near_cnt[i];
         if (threadIdx.x == 0) {                                  // the dummy well that pads odd near lists: term ~1e-100
             double *d = s_wells + ff_dummy_offset(tp.nw);
             d[0] = 1e100; d[1] = 1.0; d[2] = 1.0;
         }
-        fs.c64 = s_c64; fs.c32 = s_c32; fs.off = s_off; fs.cnt = s_cnt;
+        fs.c64 = s_c64; fs.off = s_off; fs.cnt = s_cnt;
     }
     if (FF && !CONFINED) {
         // unconfined: c64 (discharge) + p32 (potential, p_k = h c_(k-1)/k as float2) + b0 + near well indices
-        const int ntiles = ff.ntx * ff.nty, order = ff.n64;
+        const int ntiles = ff.ntx * ff.nty, order = ff.order;
         const double h = 0.7071067811865476 / ff.inv_tile;                        // tile / sqrt 2
         double2 *s_c64 = s_dyn + ff_store_double2(tp.nw);
         float2 *s_p32 = reinterpret_cast<float2 *>(s_c64 + ntiles * order);
@@ -169,7 +160,7 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
         __syncthreads();
     }
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE, FF>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
+    dopri_track<CONFINED, MODE, FF, ORD>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
 }
 
 // c[r][tile][k] = sum_w w_rw P[tile][w][k],  w_rw = q_rw / (2 pi H_r n_r)  (the scaling of stage_realization<true>).
@@ -531,46 +522,53 @@ static void prof_end(oneka_ctx *ctx)
 static size_t ff_smem(const FarFieldDev &ff)
 {
     const size_t nt = (size_t)ff.ntx * ff.nty;
-#if ONEKA_FF_COEF_GLOBAL
-    return (nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
-#else
-    return (nt * ff.n64 * sizeof(double2) + nt * ff.n32 * sizeof(float2) + nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
-#endif
+    return (nt * ff.order * sizeof(double2) + nt * ff.max_near * 4 + nt * 2 + 15) & ~(size_t)15;
 }
 
 static size_t ff_smem_unc(const FarFieldDev &ff)
 {
     const size_t nt = (size_t)ff.ntx * ff.nty;
-    return (nt * ff.n64 * (sizeof(double2) + sizeof(float2)) + nt * 8 + nt * ff.max_near * 2 + nt * 2 + 15) & ~(size_t)15;
+    return (nt * ff.order * (sizeof(double2) + sizeof(float2)) + nt * 8 + nt * ff.max_near * 2 + nt * 2 + 15) & ~(size_t)15;
+}
+
+// dynamic shared memory a far-field CTA may use so that FF_MIN_CTAS of them fit on an SM (1 KB per CTA is reserved by the
+// system; the kernel's static shared memory is ~200 B)
+static size_t ff_smem_budget(const oneka_ctx *ctx, int min_ctas) { return ctx->smem_per_sm / (size_t)min_ctas - 1024 - 512; }
+
+template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS>
+static int launch_one(oneka_ctx *ctx, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps, const FarFieldDev &ff, size_t smem)
+{
+    const long long nblk = tp.R * ((tp.P + THREADS - 1) / THREADS);
+    if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
+    auto kern = track_kernel<CONFINED, MODE, FF, ORD, THREADS, MIN_CTAS>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nblk, THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ff);
+    return ONEKA_OK;
 }
 
 template <int MODE>
 static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps,
                         const FarFieldDev *ff = nullptr)
 {
-    const int chunks = (tp.P + TRACK_THREADS - 1) / TRACK_THREADS;
-    const long long nblk = tp.R * chunks;
-    if (nblk <= 0) return ONEKA_OK;
-    if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
+    if (tp.R <= 0) return ONEKA_OK;
     size_t smem = track_smem(tp.nw);
     if (ff) smem += m->confined ? ff_smem(*ff) : ff_smem_unc(*ff);
     if (smem > 200 * 1024) return fail(ONEKA_ERR_ARG, "nw = %d wells do not fit in shared memory", tp.nw);
     prof_begin(ctx, 0);
     FarFieldDev none;
     memset(&none, 0, sizeof(none));
-    if (m->confined && ff) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<true, MODE, true><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, *ff);
-    } else if (m->confined) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<true, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<true, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
-    } else if (ff) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<false, MODE, true><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, *ff);
-    } else {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(track_kernel<false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<false, MODE, false><<<(unsigned)nblk, TRACK_THREADS, smem, ctx->stream>>>(tp, L, bitmaps, none);
-    }
+    int rc;
+    if (m->confined && ff && ff->order == FF_ORDER_UNROLLED)
+        rc = launch_one<true, MODE, true, FF_ORDER_UNROLLED, FF_THREADS, FF_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+    else if (m->confined && ff)
+        rc = launch_one<true, MODE, true, 0, FF_THREADS, FF_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+    else if (m->confined)
+        rc = launch_one<true, MODE, false, 0, TRACK_THREADS, TRACK_MIN_CTAS>(ctx, tp, L, bitmaps, none, smem);
+    else if (ff)
+        rc = launch_one<false, MODE, true, 0, FF_UNC_THREADS, FF_UNC_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+    else
+        rc = launch_one<false, MODE, false, 0, TRACK_THREADS, TRACK_MIN_CTAS>(ctx, tp, L, bitmaps, none, smem);
+    if (rc) return rc;
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -585,7 +583,7 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     const oneka_ctx::FarField &f = ctx->ff;
     use = f.on && (m->confined || f.unconfined) && m->nw == f.nw && m->xo == f.xo && m->yo == f.yo && nr > 0;
     if (!use) return ONEKA_OK;
-    if (!m->confined && track_smem(f.nw) + (((size_t)f.ntx * f.nty * f.order * 24 + (size_t)f.ntx * f.nty * (10 + 2 * f.max_near) + 15) & ~(size_t)15) > 200 * 1024) {
+    if (!m->confined && f.smem_unconfined > 200 * 1024) {
         use = false;                                                  // the unconfined tables (c64 + p32) do not fit: direct sums
         return ONEKA_OK;
     }
@@ -614,11 +612,10 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     }
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    out.ntx = f.ntx; out.nty = f.nty; out.n64 = f.n64; out.n32 = f.order - f.n64; out.max_near = f.max_near;
+    out.ntx = f.ntx; out.nty = f.nty; out.order = f.order; out.max_near = f.max_near;
     out.gx0 = f.gx0; out.gy0 = f.gy0; out.inv_tile = 1.0 / f.tile;
     out.coef = ctx->ff.coef; out.near_off = f.near_off; out.near_cnt = f.near_cnt;
     out.b0 = m->confined ? nullptr : ctx->ff.b0; out.near_idx = f.near_idx; out.near_raw = f.near_raw;
-    if (!m->confined) { out.n64 = f.order; out.n32 = 0; }
     return ONEKA_OK;
 }
 
@@ -749,6 +746,7 @@ oneka_ctx *oneka_create(int device)
     if (!ctx) { fail(ONEKA_ERR_NOMEM, "out of host memory"); return nullptr; }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (cudaMalloc(&ctx->stats_dev, N_STATS * sizeof(unsigned long long)) != cudaSuccess) {
         fail(ONEKA_ERR_NOMEM, "cudaMalloc(stats) failed"); delete ctx; return nullptr;
     }
@@ -849,13 +847,14 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     if (f.near_raw) { cudaFree(f.near_raw); f.near_raw = nullptr; }
     if (f.wells) { cudaFree(f.wells); f.wells = nullptr; }
     if (nw <= 0 || order <= 0) return ONEKA_OK;                        // switched off
+    if (order < 2 || (order & 1)) return fail(ONEKA_ERR_ARG, "far field: order must be even and >= 2 (two interleaved Horner chains)");
+    (void)order_fp64;                                                  // (ABI slot of the dropped FP32 tail)
     FFTables T;
     if (const char *why = build_ff_tables(nw, well_xy_host, xo, yo, x0 - xo, y0 - yo, tile, ntx, nty, order, eta, T))
         return fail(ONEKA_ERR_ARG, "%s", why);
     FarFieldDev probe;
     memset(&probe, 0, sizeof(probe));
-    const int n64 = ff_split(order, eta, order_fp64);
-    probe.ntx = ntx; probe.nty = nty; probe.n64 = n64; probe.n32 = order - n64; probe.max_near = T.max_near;
+    probe.ntx = ntx; probe.nty = nty; probe.order = order; probe.max_near = T.max_near;
     if (track_smem(nw) + ff_smem(probe) > 200 * 1024)
         return fail(ONEKA_ERR_ARG, "far field: %d tiles x order %d do not fit in shared memory", T.ntiles, order);
     CUDA_TRY(cudaMalloc(&f.P, T.P.size() * sizeof(double2)));
@@ -872,11 +871,27 @@ int oneka_set_farfield(oneka_ctx *ctx, int32_t nw, const double *well_xy_host, d
     CUDA_TRY(cudaMemcpy(f.near_raw, T.cnt_raw.data(), T.cnt_raw.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&f.wells, (size_t)nw * 2 * sizeof(double)));
     CUDA_TRY(cudaMemcpy(f.wells, well_xy_host, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice));
-    f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.n64 = n64; f.max_near = T.max_near;
+    f.nw = nw; f.ntx = ntx; f.nty = nty; f.order = order; f.max_near = T.max_near;
+    f.smem_confined = track_smem(nw) + ff_smem(probe);
+    f.smem_unconfined = track_smem(nw) + ff_smem_unc(probe);
     f.xo = xo; f.yo = yo; f.gx0 = x0 - xo; f.gy0 = y0 - yo; f.tile = tile; f.eta = eta; f.mean_near = T.mean_near;
     f.on = true;
     if (max_near_out) *max_near_out = T.max_near;
     if (mean_near_out) *mean_near_out = T.mean_near;
+    return ONEKA_OK;
+}
+
+int oneka_farfield_info(oneka_ctx *ctx, int32_t *ntiles, int32_t *order, int32_t *max_near, uint64_t *smem_confined,
+                        uint64_t *smem_unconfined, uint64_t *smem_budget)
+{
+    if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
+    const oneka_ctx::FarField &f = ctx->ff;
+    if (ntiles) *ntiles = f.on ? f.ntx * f.nty : 0;
+    if (order) *order = f.on ? f.order : 0;
+    if (max_near) *max_near = f.on ? f.max_near : 0;
+    if (smem_confined) *smem_confined = f.on ? f.smem_confined : 0;
+    if (smem_unconfined) *smem_unconfined = f.on ? f.smem_unconfined : 0;
+    if (smem_budget) *smem_budget = ff_smem_budget(ctx, FF_MIN_CTAS);
     return ONEKA_OK;
 }
 
@@ -897,16 +912,8 @@ int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const doubl
         return fail(ONEKA_ERR_ARG, "%s", why);
     std::vector<double2> coef;
     ff_host_coefficients(T, nw, order, w_host, coef);
-    // the split the device uses: low orders double2, the tail rounded to float2 (track_kernel's staging)
-    const int n64 = ff_split(order, eta, order_fp64), n32 = order - n64;
-    std::vector<float2> c32((size_t)T.ntiles * (n32 > 0 ? n32 : 1));
-    std::vector<double2> c64((size_t)T.ntiles * n64);
-    for (int t = 0; t < T.ntiles; ++t)
-        for (int k = 0; k < order; ++k) {
-            const double2 c = coef[(size_t)t * order + k];
-            if (k < n64) c64[(size_t)t * n64 + k] = c;
-            else c32[(size_t)t * n32 + (k - n64)] = make_float2((float)c.x, (float)c.y);
-        }
+    if (order < 2 || (order & 1)) return fail(ONEKA_ERR_ARG, "far field: order must be even and >= 2");
+    (void)order_fp64;
     const double gx0 = x0 - xo, gy0 = y0 - yo, inv_tile = 1.0 / tile;
     for (int64_t i = 0; i < npts; ++i) {
         const double dx0 = pts_host[2 * i] - xo, dy0 = pts_host[2 * i + 1] - yo;
@@ -924,10 +931,8 @@ int oneka_farfield_eval_host(int32_t nw, const double *well_xy_host, const doubl
         } else {
             for (int j = T.near_begin[tile_i]; j < T.near_begin[tile_i + 1]; ++j) direct(T.near_flat[j]);
             double re, im;
-            float tr = 0.0f, ti = 0.0f;
-            if (n32 > 0) ff_tail_eval(c32.data() + (size_t)tile_i * n32, n32, (float)zr, (float)zi, tr, ti);
-            if (n32 > 0) ff_poly_eval<true>(c64.data() + (size_t)tile_i * n64, n64, zr, zi, (double)tr, (double)ti, re, im);
-            else ff_poly_eval<false>(c64.data() + (size_t)tile_i * n64, n64, zr, zi, 0.0, 0.0, re, im);
+            if (order == FF_ORDER_UNROLLED) ff_poly_eval<FF_ORDER_UNROLLED>(coef.data() + (size_t)tile_i * order, order, zr, zi, re, im);
+            else ff_poly_eval<0>(coef.data() + (size_t)tile_i * order, order, zr, zi, re, im);
             gx += re;
             gy -= im;
             if (near_count_out) near_count_out[i] = T.near_begin[tile_i + 1] - T.near_begin[tile_i];
@@ -1094,7 +1099,7 @@ static int capture_impl(oneka_ctx *ctx, const oneka_model_desc *m, const oneka_l
         if (rc) return rc;
     }
     // keep each launch below 2^31 CTAs
-    const int chunks = (P + TRACK_THREADS - 1) / TRACK_THREADS;
+    const int chunks = (P + TRACK_THREADS - 1) / TRACK_THREADS;      // (the smallest CTA shape: the most CTAs)
     const long long max_r = 0x7fffffffLL / chunks;
     if (slots > max_r) slots = max_r;
     slots = farfield_batch(ctx, slots);

@@ -175,10 +175,6 @@ __device__ __forceinline__ void rcp_parts(double a, double &y0, double &t)
 //   same discharge (9 FP64 per well: the squared distance itself is needed), plus
 //   Phi = A dx^2 + B dy^2 + C dx dy + D dx + E dy + F + sum q ln(r^2)/(4 pi), head from Phi (two regimes), saturated
 //   thickness min(head, H); Phi <= 0 or head <= 0 is the reference's AquiferError -> PATH_AQUIFER_DRY.
-// LDS.128 of the next block issued ahead (0, 2, 3 or 6; measured: 2 = 6 = +2 % over 0 on C3 and C4)
-#ifndef ONEKA_LDS_PREFETCH
-#define ONEKA_LDS_PREFETCH 2
-#endif
 constexpr int SWELL_BLK = 12;        // confined store: blocks of 4 wells x {b, cx, cy} = 6 LDS.128
 // confined, scaled: one well = 8 FP64-pipe instructions + MUFU.RCP64H
 __device__ __forceinline__ void scaled_term(double dx0, double dy0, double b, double cx, double cy, double &gx, double &gy)
@@ -223,9 +219,9 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
     if (CONFINED) {
         const double *p = s_wells;
         const double *const pend = s_wells + (nw >> 2) * SWELL_BLK;
-#if ONEKA_LDS_PREFETCH == 2
         // the first two LDS.128 of the NEXT block (its first well) are issued while the current block is computed (the
-        // store has a block of slack): the first chain of an iteration no longer waits for shared memory
+        // store has a block of slack): the first chain of an iteration no longer waits for shared memory.  Measured on B200
+        // (profiles/r01_notes.md): +2 % over no prefetch on C3 and C4; prefetching 3 or all 6 loads is no better.
         double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1];
 #pragma unroll 1
         for (; p != pend; p += SWELL_BLK) {
@@ -239,50 +235,6 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
             scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
             scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
         }
-#elif ONEKA_LDS_PREFETCH == 3
-        double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1], n2 = reinterpret_cast<const double2 *>(p)[2];
-#pragma unroll 1
-        for (; p != pend; p += SWELL_BLK) {
-            const double2 v0 = n0, v1 = n1, v2 = n2;
-            const double2 v3 = reinterpret_cast<const double2 *>(p)[3];
-            const double2 v4 = reinterpret_cast<const double2 *>(p)[4], v5 = reinterpret_cast<const double2 *>(p)[5];
-            n0 = reinterpret_cast<const double2 *>(p)[6];
-            n1 = reinterpret_cast<const double2 *>(p)[7];
-            n2 = reinterpret_cast<const double2 *>(p)[8];
-            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
-            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
-            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
-            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
-        }
-#elif ONEKA_LDS_PREFETCH == 6
-        double2 n0 = reinterpret_cast<const double2 *>(p)[0], n1 = reinterpret_cast<const double2 *>(p)[1], n2 = reinterpret_cast<const double2 *>(p)[2];
-        double2 n3 = reinterpret_cast<const double2 *>(p)[3], n4 = reinterpret_cast<const double2 *>(p)[4], n5 = reinterpret_cast<const double2 *>(p)[5];
-#pragma unroll 1
-        for (; p != pend; p += SWELL_BLK) {
-            const double2 v0 = n0, v1 = n1, v2 = n2, v3 = n3, v4 = n4, v5 = n5;
-            n0 = reinterpret_cast<const double2 *>(p)[6];
-            n1 = reinterpret_cast<const double2 *>(p)[7];
-            n2 = reinterpret_cast<const double2 *>(p)[8];
-            n3 = reinterpret_cast<const double2 *>(p)[9];
-            n4 = reinterpret_cast<const double2 *>(p)[10];
-            n5 = reinterpret_cast<const double2 *>(p)[11];
-            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
-            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
-            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
-            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
-        }
-#else
-#pragma unroll 1
-        for (; p != pend; p += SWELL_BLK) {
-            const double2 v0 = reinterpret_cast<const double2 *>(p)[0], v1 = reinterpret_cast<const double2 *>(p)[1];
-            const double2 v2 = reinterpret_cast<const double2 *>(p)[2], v3 = reinterpret_cast<const double2 *>(p)[3];
-            const double2 v4 = reinterpret_cast<const double2 *>(p)[4], v5 = reinterpret_cast<const double2 *>(p)[5];
-            scaled_term(dx0, dy0, v0.x, v0.y, v1.x, gx, gy);
-            scaled_term(dx0, dy0, v1.y, v2.x, v2.y, gx, gy);
-            scaled_term(dx0, dy0, v3.x, v3.y, v4.x, gx, gy);
-            scaled_term(dx0, dy0, v4.y, v5.x, v5.y, gx, gy);
-        }
-#endif
         const int rem = nw & 3;
         if (rem > 0) scaled_term(dx0, dy0, p[0], p[1], p[2], gx, gy);
         if (rem > 1) scaled_term(dx0, dy0, p[3], p[4], p[5], gx, gy);
@@ -383,7 +335,7 @@ __device__ __forceinline__ int field_feval(const RealConsts &rc, const double *_
 // beyond rounding (~1e-15 relative to sum |terms|).
 struct FarFieldDev {
     int ntx, nty;
-    int n64, n32;                    // terms evaluated in FP64 (even, >= 2) and in FP32 (the tail, >= 0): order = n64 + n32
+    int order;                       // terms of the polynomial (even, >= 2)
     int max_near;                    // even (lists are padded with the dummy well)
     double gx0, gy0;                 // lower-left corner of the tile grid, relative to (xo, yo)
     double inv_tile;                 // 1 / tile side
@@ -396,155 +348,80 @@ struct FarFieldDev {
     const unsigned short *near_raw;  // [ntx*nty]            their counts
 };
 struct FarFieldShared {
-    const double2 *c64; const float2 *c32; const unsigned int *off; const unsigned short *cnt;
+    const double2 *c64; const unsigned int *off; const unsigned short *cnt;
     // unconfined flow: the potential's polynomial p_k = h c_(k-1)/k (k = 1..order) as float2, b0 per tile, near well indices
     const float2 *p32; const double *b0; const unsigned short *idx; const unsigned short *raw;
 };
 // shared-memory layout of a tracking CTA:
-//   [well store + 256 B of slack][c64 ntiles x n64 double2][c32 ntiles x n32 float2][near_off][near_cnt];
+//   [well store + 256 B of slack][c64 ntiles x order double2][near_off][near_cnt];
 // the dummy well {b = 1e100, c = (1, 1)} that pads odd near lists sits in the slack right behind the confined store
 __host__ __device__ __forceinline__ constexpr int ff_dummy_offset(int nw) { return ((nw + 3) >> 2) * 12; }                    // doubles
 __host__ __device__ __forceinline__ constexpr int ff_store_double2(int nw) { return (((nw + 3) >> 2) * 14 * 8 + 256) / 16; }  // double2s
 
 constexpr double FF_SQRT2 = 1.4142135623730951;
 
-// Build knobs, all measured on B200 (profiles/r01_farfield_ab.txt; C3 perham / C4 200 wells, ms per step):
-//   defaults (all-FP64 polynomial, F2I / I2F tile lookup, no prefetch)        79.7 / 33.0
-//   ONEKA_FF_TAIL 1        high-order terms in FP32 (below)                    87.1 / 36.0   more code, more spills
-//   ONEKA_FF_LOCATE_CVT 0  tile index by the 1.5 * 2^52 trick                  84.8 / 34.9   + 9 instructions per evaluation
-//   ONEKA_FF_PREFETCH 1    next trip's coefficients loaded ahead               86.9 / 35.5   164 B of spills instead of 68
-//   evaluation as a __noinline__ call (half the code)                        105.6 / 42.9
-// The kernel sits at 80 registers with the Runge-Kutta stages live; whatever adds live values to the evaluation loses.
-#ifndef ONEKA_FF_TAIL
-#define ONEKA_FF_TAIL 0
-#endif
-#ifndef ONEKA_FF_LOCATE_CVT
-#define ONEKA_FF_LOCATE_CVT 1
-#endif
-#ifndef ONEKA_FF_PREFETCH
-#define ONEKA_FF_PREFETCH 0
-#endif
-// ONEKA_FF_COEF_GLOBAL 1 (NOT yet timed on hardware -- prepared for the next round): the coefficient tables stay in global
-// memory and are read through L1 (ld.global.nc); shared memory then holds only the near lists, so the tile count is no longer
-// bounded by it (256 tiles of ~110 m: ~0.7 near wells per evaluation at C3 instead of 2, and a lower order suffices).
-#ifndef ONEKA_FF_COEF_GLOBAL
-#define ONEKA_FF_COEF_GLOBAL 0
-#endif
-// THE FP32 TAIL (ONEKA_FF_TAIL).  |c_k| <= S eta^k (S = sum over the far wells of |w|/|z_w - z_c|), so the terms k >= n64 with
-// eta^n64 <= 2^-24 contribute at most 2^-24 S: evaluated in FP32 (FFMA: half the issue cost of DFMA, on the otherwise idle
-// FP32 pipe) their rounding error is ~2^-23 x 2^-24 S = 7e-15 S, the level of the truncation itself.
-//   T = sum_{j < n} t_j zeta^j   (t_j = c_{n64 + j} as float2),  Horner, one chain
-template <typename F2>
-__host__ __device__ __forceinline__ void ff_tail_eval(const F2 *t, int n, float fr, float fi, float &tr, float &ti)
-{
-    float ar = 0.0f, ai = 0.0f;
-#pragma unroll 2
-    for (int j = n - 1; j >= 0; --j) {
-        const F2 c = t[j];
-        const float nr = fmaf(ar, fr, fmaf(-ai, fi, c.x));
-        const float ni = fmaf(ar, fi, fmaf(ai, fr, c.y));
-        ar = nr; ai = ni;
-    }
-    tr = ar; ti = ai;
-}
+// What was built, timed on B200 and dropped (C3 perham / C4 200 wells, ms per step; profiles/r01_farfield_ab*.txt, r02_knob_scan*.txt):
+// high-order terms in FP32 (87.1 / 36.0 against 79.7 / 33.0: conversions, a second loop, more live values), the tile index by the
+// 1.5 * 2^52 trick instead of F2I / I2F (84.8 / 34.9), the next trip's coefficients loaded ahead (86.9 / 35.5, and again slower
+// with 128 registers), the evaluation as a __noinline__ call (105.6 / 42.9), the coefficient tables read in place through L1
+// (93.7 / 37.9), the six Runge-Kutta stages as one loop with the stage derivatives in local memory (85.0 / 36.0).
+// What won (round 2): MORE TILES and a LOWER ORDER at the same truncation -- 256-thread CTAs, two per SM, leave 104 KB of shared
+// memory for a realization's table (380 tiles of order 16, eta 0.15) -- and the Horner loop unrolled at that order:
+// 79.9 / 33.1 -> 64.6 / 25.6.
 
-// sum_{k < n64} c_k zeta^k + zeta^n64 (sr + i si): two interleaved Horner chains in w = zeta^2 (even / odd powers, half the
-// dependency depth); the tail value seeds the even chain as the coefficient of w^(n64/2)
-// `c` is anything indexable that yields {x, y}: a pointer to double2, or CoefLdg (read-only global loads through L1)
-template <bool SEED, typename CP>
-__host__ __device__ __forceinline__ void ff_poly_eval(CP c, int n64, double zr, double zi, double sr, double si,
-                                                      double &re, double &im)
+// sum_{k < n} c_k zeta^k: two interleaved Horner chains in w = zeta^2 (even / odd powers, half the dependency depth).
+// ORD > 0: the order is the compile-time constant ORD and the loop is unrolled (no loop control, no address arithmetic: 5 of
+// the 25 instructions of a trip); ORD == 0: n terms at run time.  n even, >= 2.
+template <int ORD>
+__host__ __device__ __forceinline__ void ff_poly_eval(const double2 *__restrict__ c, int n, double zr, double zi, double &re, double &im)
 {
-    typedef double2 C2;
+    if (ORD > 0) n = ORD;
     const double wr = fma(zr, zr, -(zi * zi));
     const double wi = 2.0 * (zr * zi);
-    const C2 ct = c[n64 - 2], cu = c[n64 - 1];
+    const double2 ct = c[n - 2], cu = c[n - 1];
     double er = ct.x, ei = ct.y;
-    if (SEED) { er = fma(sr, wr, fma(-si, wi, ct.x)); ei = fma(sr, wi, fma(si, wr, ct.y)); }
     double orr = cu.x, oi = cu.y;
-#if ONEKA_FF_PREFETCH
-    // software-pipelined: the coefficients of the next trip are loaded before the current trip's eight FMAs
-    if (n64 >= 4) {
-        C2 ce = c[n64 - 4], co = c[n64 - 3];
-#pragma unroll 2
-        for (int k = n64 - 4; k >= 2; k -= 2) {
-            const C2 ne = c[k - 2], no = c[k - 1];
-            const double ner = fma(er, wr, fma(-ei, wi, ce.x));
-            const double nei = fma(er, wi, fma(ei, wr, ce.y));
-            const double nor = fma(orr, wr, fma(-oi, wi, co.x));
-            const double noi = fma(orr, wi, fma(oi, wr, co.y));
-            er = ner; ei = nei; orr = nor; oi = noi;
-            ce = ne; co = no;
-        }
+    auto trip = [&](int k) {
+        const double2 ce = c[k], co = c[k + 1];
         const double ner = fma(er, wr, fma(-ei, wi, ce.x));
         const double nei = fma(er, wi, fma(ei, wr, ce.y));
         const double nor = fma(orr, wr, fma(-oi, wi, co.x));
         const double noi = fma(orr, wi, fma(oi, wr, co.y));
         er = ner; ei = nei; orr = nor; oi = noi;
-    }
-#else
+    };
+    if (ORD > 0) {
+#pragma unroll
+        for (int k = ORD - 4; k >= 0; k -= 2) trip(k);
+    } else {
 #pragma unroll 2
-    for (int k = n64 - 4; k >= 0; k -= 2) {
-        const C2 ce = c[k], co = c[k + 1];
-        const double ner = fma(er, wr, fma(-ei, wi, ce.x));
-        const double nei = fma(er, wi, fma(ei, wr, ce.y));
-        const double nor = fma(orr, wr, fma(-oi, wi, co.x));
-        const double noi = fma(orr, wi, fma(oi, wr, co.y));
-        er = ner; ei = nei; orr = nor; oi = noi;
+        for (int k = n - 4; k >= 0; k -= 2) trip(k);
     }
-#endif
     re = fma(orr, zr, fma(-oi, zi, er));
     im = fma(orr, zi, fma(oi, zr, ei));
 }
 
-// tile of the point (dx0, dy0) [relative to (xo, yo)] and its scaled offset from the tile centre; false = outside the grid.
-// floor() by the 1.5 * 2^52 trick (no F2I / I2F of the quarter-rate conversion pipe): m = (u - 0.5) + MAGIC rounds to the
-// integer nearest u - 0.5, whose low word is the tile index.  On an exact tile boundary ties-to-even may pick either
-// neighbour; both expansions hold there (|zeta| <= 1 on the closed tile).
-__host__ __device__ __forceinline__ int ff_lo32(double m)
-{
-#ifdef __CUDA_ARCH__
-    return __double2loint(m);
-#else
-    long long b;
-    memcpy(&b, &m, 8);
-    return (int)(unsigned int)(b & 0xffffffffLL);
-#endif
-}
+// tile of the point (dx0, dy0) [relative to (xo, yo)] and its scaled offset from the tile centre; false = outside the grid
+// (or nan).  On an exact tile boundary either neighbour would do: both expansions hold on the closed tile.
 __host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0, double gy0, double inv_tile,
                                                    double dx0, double dy0, int &tile, double &zr, double &zi)
 {
     const double ux = (dx0 - gx0) * inv_tile, uy = (dy0 - gy0) * inv_tile;
-#if ONEKA_FF_LOCATE_CVT
     if (!(ux >= 0.0 && ux < (double)ntx && uy >= 0.0 && uy < (double)nty)) return false;      // also nan
     const int ci = (int)ux, cj = (int)uy;                                                      // trunc = floor for u >= 0
     tile = cj * ntx + ci;
-    zr = (ux - (double)ci - 0.5) * FF_SQRT2;
+    zr = (ux - (double)ci - 0.5) * FF_SQRT2;                                                   // (x - x_c)/h,  h = tile/sqrt 2
     zi = (uy - (double)cj - 0.5) * FF_SQRT2;
-    return true;
-#endif
-    constexpr double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
-    if (!(fabs(ux) < 1e9 && fabs(uy) < 1e9)) return false;                 // far away or nan: the trick needs |u| < 2^31
-    const double mx = (ux - 0.5) + MAGIC, my = (uy - 0.5) + MAGIC;
-    const int ti = ff_lo32(mx), tj = ff_lo32(my);
-    if ((unsigned int)ti >= (unsigned int)ntx || (unsigned int)tj >= (unsigned int)nty) return false;
-    tile = tj * ntx + ti;
-    zr = fma(ux - (mx - MAGIC), FF_SQRT2, -0.5 * FF_SQRT2);                // (x - x_c)/h,  h = tile/sqrt 2
-    zi = fma(uy - (my - MAGIC), FF_SQRT2, -0.5 * FF_SQRT2);
     return true;
 }
 
 #if defined(__CUDACC__) || defined(ONEKA_EMU)
-struct CoefLdg {
-    const double2 *p;
-    __device__ __forceinline__ double2 operator[](int k) const { return __ldg(p + k); }
-};
 // the direct sum as an out-of-line call: the rare particle outside the tile grid
 __device__ __noinline__ void field_direct_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
 {
     field_feval<true>(rc, s_wells, nw, x, y, fx, fy);
 }
 
+template <int ORD>
 __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
                                               const FarFieldDev &ff, const FarFieldShared &fs,
                                               double x, double y, double &fx, double &fy)
@@ -559,11 +436,6 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     }
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
-    // far wells, high orders: FP32
-    float tr = 0.0f, ti = 0.0f;
-#if ONEKA_FF_TAIL
-    if (ff.n32 > 0) ff_tail_eval(fs.c32 + tile * ff.n32, ff.n32, (float)zr, (float)zi, tr, ti);
-#endif
     // near wells, two per trip (lists are padded to even length with the dummy well, whose term is ~1e-100)
     const unsigned int *po = fs.off + tile * ff.max_near;
     const int n = fs.cnt[tile];
@@ -576,19 +448,15 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
         scaled_term(dx0, dy0, p0[0], p0[1], p0[2], gx, gy);
         scaled_term(dx0, dy0, p1[0], p1[1], p1[2], hx, hy);
     }
-    // far wells, low orders: FP64, seeded with the tail
+    // far wells: the tile's polynomial
     double re, im;
-#if ONEKA_FF_COEF_GLOBAL
-    ff_poly_eval<ONEKA_FF_TAIL != 0>(CoefLdg{fs.c64 + tile * ff.n64}, ff.n64, zr, zi, (double)tr, (double)ti, re, im);
-#else
-    ff_poly_eval<ONEKA_FF_TAIL != 0>(fs.c64 + tile * ff.n64, ff.n64, zr, zi, (double)tr, (double)ti, re, im);
-#endif
+    ff_poly_eval<ORD>(fs.c64 + tile * (ORD > 0 ? ORD : ff.order), ff.order, zr, zi, re, im);
     fx = (gx + hx) + re;
     fy = (gy + hy) - im;
     return PATH_OK;
 }
 
-// ---- unconfined flow through the far field (opt-in: oneka_set_farfield_unconfined; timed next round) ---------------------------
+// ---- unconfined flow through the far field (oneka_set_farfield_unconfined) -------------------------------------------------
 // field_feval<false> needs, besides the discharge, the POTENTIAL -- but only to decide whether the aquifer is fully saturated at
 // the point (then V = Q/(H n) whatever Phi is), which an FP32-accurate value settles almost everywhere.  The far wells' part of it,
 //     sum_far w ln|z - z_w| = b0 + Re sum_{k>=1} p_k zeta^k,     b0 = sum_far w ln|z_w - z_c|,   p_k = h c_(k-1) / k,
@@ -623,9 +491,9 @@ __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const do
                   reinterpret_cast<const float *>(s_wells + (w >> 2) * WELL_BLK + 12)[w & 3], gx, gy, lsum32);
     }
     // far wells: discharge polynomial in FP64 ...
-    const int order = ff.n64;
+    const int order = ff.order;
     double re, im;
-    ff_poly_eval<false>(fs.c64 + tile * order, order, zr, zi, 0.0, 0.0, re, im);
+    ff_poly_eval<0>(fs.c64 + tile * order, order, zr, zi, re, im);
     gx += re;
     gy -= im;
     // ... and their potential in FP32:  Re(zeta T),  T = sum_j p_(j+1) zeta^j
@@ -698,12 +566,6 @@ struct RasterCounters { unsigned int clipped, exact; };
 // [0, ncols) x [0, nrows); the exact emulation of the auto-expanding field passes the window the reference's grid
 // had when this path was inserted (oneka_capture_clipped).
 struct ClipWin { int l, r, b, t; };
-
-// windows narrower than this use the node loop for every row (0 = scan-line rows always; measured on B200:
-// always-on is 8 % faster than node-only at 7-column windows (C3) and 33 % faster at 15 columns (C5))
-#ifndef ONEKA_SCAN_MIN_COLS
-#define ONEKA_SCAN_MIN_COLS 0
-#endif
 
 // MUFU.SQRT (nan for negative arguments, as the callers expect)
 __device__ __forceinline__ float sqrt_fast(float a)
@@ -818,10 +680,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     const float cr = fmaf(kk, m, uy);
     const float kisy = kk * isy;
     const float ylo = fminf(0.0f, fbay), yhi = fmaxf(0.0f, fbay);
-#ifndef ONEKA_TAU_REL
-#define ONEKA_TAU_REL 1e-3f
-#endif
-    const float tau = fmaxf(ONEKA_TAU_REL * u, 256.0f * EPS32 * Lm);
+    const float tau = fmaxf(1e-3f * u, 256.0f * EPS32 * Lm);
     const float k_edge = 4.0f * EPS32 * Lm * fmaf(17.0f, fabsf(m), 11.0f) * L.inv_dx32;     // [cells]
     const float k_cap = 40.0f * EPS32 * Lm * Lm * L.inv_dx32;                                // [cells * m]
     const int ncol = right - left;
@@ -830,7 +689,8 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     // so only the rows that do cross a straight edge fall back to the node loop (edge_ok false; also for sy = 0, where
     // m and k_edge are inf or nan).
     const bool edge_ok = k_edge < 0.125f;
-    const bool scan_ok = !all_exact && ncol >= ONEKA_SCAN_MIN_COLS && u > 0.0f;
+    // (scan-line rows for every window width: measured 8 % faster than the node loop at 7-column windows (C3), 33 % at 15 (C5))
+    const bool scan_ok = !all_exact && u > 0.0f;
 
     unsigned int *row = bm + (size_t)bottom * L.wpr;
     float fi = 0.0f;
@@ -930,28 +790,11 @@ __device__ __forceinline__ unsigned long long dkey(double v)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
 
-// ONEKA_RK_LOOP 1 (NOT yet timed on hardware -- prepared for the next round, validated for arithmetic by tests/emu): the six
-// stage evaluations of an attempt as ONE loop instead of six inlined copies.  With the far field on, the unrolled kernel is
-// 4100 SASS instructions (66 KB) and ncu shows instruction-fetch stalls (no_instruction 0.72 per issue) and ~40 spill
-// instructions per attempt; the loop keeps the stage derivatives in local memory by design.
-#ifndef ONEKA_RK_LOOP
-#define ONEKA_RK_LOOP 0
-#endif
-#if ONEKA_RK_LOOP
-// rows 2..7 of the Dormand-Prince tableau (capturezone.py:202-207), six entries each, zero padded
-__constant__ double c_dopri_a[36] = {
-    1.0 / 5.0, 0, 0, 0, 0, 0,
-    3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0,
-    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0,
-    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0,
-    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0,
-    35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0};
-#endif
-
 // ------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
-template <bool CONFINED, int MODE, bool FF = false>
+//   FF: the far-field evaluation (confined: field_feval_ff<ORD>, ORD = compile-time order or 0; unconfined: field_feval_ff_unc)
+template <bool CONFINED, int MODE, bool FF = false, int ORD = 0>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
                                             long long r, int p, bool active,
@@ -959,7 +802,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 {
     // the velocity: direct sum over the wells, or (FF, confined only) near wells + the tile's far-field polynomial
     auto feval = [&](double px, double py, double &ox, double &oy) -> int {
-        if constexpr (FF && CONFINED) return field_feval_ff(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
+        if constexpr (FF && CONFINED) return field_feval_ff<ORD>(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
         else if constexpr (FF) return field_feval_ff_unc(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
         else return field_feval<CONFINED>(rc, s_wells, tp.nw, px, py, ox, oy);
     };
@@ -973,7 +816,6 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
     constexpr double e0 = 71.0 / 57600.0, e1 = -1.0 / 40.0, e2 = -71.0 / 16695.0, e3 = 71.0 / 1920.0, e4 = -17253.0 / 339200.0, e5 = 22.0 / 525.0;
     constexpr double EPS = DBL_EPSILON;                                   // :200
 
-    const int nw = tp.nw;
     const double duration = tp.duration, tol = tp.tol, maxstep = tp.maxstep;
     const double adur = fabs(duration);
 
@@ -1022,36 +864,6 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
                 ++nattempt;
                 if (fabs(t + dt) > adur) dt = duration - t;                // :223-224
 
-#if ONEKA_RK_LOOP
-                // ONE copy of the velocity evaluation: stages 2..7 in a loop, the stage derivatives in a per-thread array
-                // (local memory, L1-resident), the tableau rows from constant memory.  Same operations in the same order as the
-                // unrolled form below (the zero a71 adds fma(0, k2, .) = identity), so the step sequence is unchanged.
-                double2 kk[7];
-                kk[0] = make_double2(k1x, k1y);
-                double xt = x, yt = y;
-                bool bad = false;
-#pragma unroll 1
-                for (int s = 1; s <= 6; ++s) {
-                    const double *a = c_dopri_a + 6 * (s - 1);
-                    double sx = a[0] * kk[0].x, sy = a[0] * kk[0].y;
-#pragma unroll 1
-                    for (int j = 1; j < s; ++j) {
-                        const double2 kj = kk[j];
-                        sx = fma(a[j], kj.x, sx);
-                        sy = fma(a[j], kj.y, sy);
-                    }
-                    xt = fma(dt, sx, x);
-                    yt = fma(dt, sy, y);
-                    double ox, oy;
-                    const int st = feval(xt, yt, ox, oy);
-                    if (!CONFINED && st) { status = st; running = false; bad = true; break; }
-                    kk[s] = make_double2(ox, oy);
-                }
-                if (bad) break;
-                const double k2x = kk[1].x, k2y = kk[1].y, k3x = kk[2].x, k3y = kk[2].y, k4x = kk[3].x, k4y = kk[3].y;
-                const double k5x = kk[4].x, k5y = kk[4].y, k6x = kk[5].x, k6y = kk[5].y, k7x = kk[6].x, k7y = kk[6].y;
-                (void)k2x; (void)k2y;
-#else
                 double k2x, k2y, k3x, k3y, k4x, k4y, k5x, k5y, k6x, k6y, k7x, k7y;
                 int st;
                 st = feval(fma(dt, a20 * k1x, x), fma(dt, a20 * k1y, y), k2x, k2y);      // :227
@@ -1076,7 +888,6 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
                 st = feval(xt, yt, k7x, k7y);                                            // :236
                 if (!CONFINED && st) { status = st; running = false; break; }
 
-#endif
                 const double ex = dt * fma(e5, k6x, fma(e4, k5x, fma(e3, k4x, fma(e2, k3x, fma(e1, k7x, e0 * k1x)))));       // :237-238
                 const double ey = dt * fma(e5, k6y, fma(e4, k5y, fma(e3, k4y, fma(e2, k3y, fma(e1, k7y, e0 * k1y)))));
                 const double est = fmax(fabs(ex), fabs(ey));

@@ -22,22 +22,6 @@ struct FFTables {
     std::vector<unsigned short> idx, cnt_raw;  // [ntiles][max_near] near WELL INDICES (unpadded lists), [ntiles] their lengths
 };
 
-// terms kept in FP64: the smallest even k with eta^k <= 2^-24 (see ff_tail_eval), at most `order`
-static inline int ff_split(int order, double eta, int order_fp64)
-{
-#if ONEKA_FF_TAIL && ONEKA_FF_COEF_GLOBAL
-#error "ONEKA_FF_COEF_GLOBAL reads double2 coefficients in place: it excludes the FP32 tail"
-#endif
-#if !ONEKA_FF_TAIL
-    (void)eta; (void)order_fp64;
-    return order;                               // this build evaluates every term in FP64
-#endif
-    if (order_fp64 > 0) { int k = (order_fp64 + 1) & ~1; return k < 2 ? 2 : (k > order ? order : k); }
-    int k = 2;
-    while (k < order && pow(eta, (double)k) > 5.9604644775390625e-08) k += 2;
-    return k > order ? order : k;
-}
-
 // returns nullptr, or the reason the arguments are unusable
 static inline const char *build_ff_tables(int nw, const double *well_xy, double xo, double yo, double gx0, double gy0, double tile,
                                           int ntx, int nty, int order, double eta, FFTables &T)

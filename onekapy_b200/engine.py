@@ -157,10 +157,14 @@ class Engine:
         # far-field compression of the well sum (oneka_set_farfield): "auto" = wherever it pays, "off" = direct sums only,
         # "force" = wherever it applies, whatever the cost model says (tests, A/B runs)
         self.farfield = "off" if os.environ.get("ONEKA_FARFIELD", "auto").lower() in ("0", "off", "no") else "auto"
-        self.farfield_order = int(os.environ.get("ONEKA_FARFIELD_ORDER", "28"))
-        self.farfield_eta = float(os.environ.get("ONEKA_FARFIELD_ETA", "0.3"))
-        self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "64"))
-        self.farfield_order_fp64 = int(os.environ.get("ONEKA_FARFIELD_FP64", "0"))      # 0 = automatic FP64 / FP32 split
+        # eta = 0.15, order 16: truncation eta^order / (1 - eta) = 8e-14 of a far term, an order of magnitude below the 1e-12 of
+        # the Newton reciprocal in the direct sum it replaces; order 16 is the one the kernel evaluates unrolled.  Tiles: as many
+        # as the shared-memory budget of a tracking CTA holds (0 = automatic; ~380 at 29 wells).  Measured on B200 against the
+        # round-1 setting (eta 0.3, order 28, 64 tiles): C3 79.9 -> 64.6 ms, C4 33.1 -> 25.6 ms per step (profiles/r02_knob_scan*.txt)
+        self.farfield_order = int(os.environ.get("ONEKA_FARFIELD_ORDER", "16"))
+        self.farfield_eta = float(os.environ.get("ONEKA_FARFIELD_ETA", "0.15"))
+        self.farfield_max_tiles = int(os.environ.get("ONEKA_FARFIELD_TILES", "0"))
+        self.farfield_order_fp64 = 0                                                   # (ABI slot of the removed FP32 tail)
         self.farfield_min_wells = 12
         # the far field for confined=False too (oneka_set_farfield_unconfined): on by default since round 2 (measured on
         # B200: 200 wells 225.9 -> 57.8 ms per 1024 x 1000 paths; 29 wells 119 -> 142 ms, which the cost model of
@@ -277,12 +281,27 @@ class Engine:
             return None
         order = int(order or self.farfield_order)
         eta = float(eta or self.farfield_eta)
-        g = farfield_grid(box, int(max_tiles or self.farfield_max_tiles))
         wxy = np.ascontiguousarray(spec.well_xy, dtype=np.float64).reshape(-1, 2)
         mx, mean = C.c_int32(0), C.c_double(0.0)
-        _cabi.check(self._L.oneka_set_farfield(self._h, len(wxy), wxy.ctypes.data, float(spec.xtarget), float(spec.ytarget),
-                                               g["x0"], g["y0"], g["tile"], g["ntx"], g["nty"], order, eta,
-                                               int(self.farfield_order_fp64), C.byref(mx), C.byref(mean)))
+        tiles = int(max_tiles or self.farfield_max_tiles)
+        auto = tiles <= 0
+        if auto:
+            # as many tiles as keep TWO tracking CTAs on an SM: [well store][tiles x (order x 16 B + near list)] <= budget
+            budget = self._ff_smem_info()["budget"]
+            store = ((len(wxy) + 3) // 4) * 112 + 256
+            per_tile = (16 if spec.confined else 24) * order + (34 if spec.confined else 28)
+            tiles = max(1, int((budget - store) // per_tile))
+        for _ in range(12):
+            g = farfield_grid(box, tiles)
+            _cabi.check(self._L.oneka_set_farfield(self._h, len(wxy), wxy.ctypes.data, float(spec.xtarget), float(spec.ytarget),
+                                                   g["x0"], g["y0"], g["tile"], g["ntx"], g["nty"], order, eta,
+                                                   0, C.byref(mx), C.byref(mean)))
+            if not auto:
+                break
+            need = self._ff_smem_info()
+            if need["confined" if spec.confined else "unconfined"] <= need["budget"] or tiles <= 4:
+                break
+            tiles = int(tiles * 0.92)                            # longer near lists than estimated: fewer tiles
         info = dict(g, order=order, eta=eta, mean_near=mean.value, max_near=int(mx.value))
         self._ff_key = (self._ff_wells_key(spec), tuple(float(v) for v in box), self._ff_settings())
         self._ff_info = info
@@ -291,6 +310,12 @@ class Engine:
     def _ff_settings(self):
         """The knobs the tables depend on besides wells and box: changing one rebuilds them."""
         return (int(self.farfield_order), float(self.farfield_eta), int(self.farfield_max_tiles), int(self.farfield_order_fp64))
+
+    def _ff_smem_info(self):
+        """Dynamic shared memory per CTA the current tables need (confined / unconfined kernel) and the budget per CTA."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _cabi.check(self._L.oneka_farfield_info(self._h, None, None, None, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(confined=int(a.value), unconfined=int(b.value), budget=int(c.value))
 
     def _ff_wells_key(self, spec):
         return (len(spec.well_xy), float(spec.xtarget), float(spec.ytarget),

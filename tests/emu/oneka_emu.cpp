@@ -125,7 +125,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
     std::memset(&ff, 0, sizeof(ff));
     if (use_ff) {
         if (build_ff_tables(nw, well_xy, xo, yo, ff_x0 - xo, ff_y0 - yo, ff_tile, ff_ntx, ff_nty, ff_order, ff_eta, T)) return -2;
-        ff.ntx = ff_ntx; ff.nty = ff_nty; ff.n64 = ff_order; ff.n32 = 0; ff.max_near = T.max_near;
+        ff.ntx = ff_ntx; ff.nty = ff_nty; ff.order = ff_order; ff.max_near = T.max_near;
         ff.gx0 = ff_x0 - xo; ff.gy0 = ff_y0 - yo; ff.inv_tile = 1.0 / ff_tile;
     }
 
@@ -139,7 +139,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
     for (long long r = 0; r < R; ++r) {
         if (confined) stage_realization<true>(tp, r, rc, s_wells.data());
         else stage_realization<false>(tp, r, rc, s_wells.data());
-        FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr};
+        FarFieldShared fs = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (use_ff && !confined) {                                                                       // track_kernel<false, ., true>'s staging
             for (int w = 0; w < nw; ++w) wsc[w] = q[(size_t)r * nw + w] * 0.15915494309189535;           // farfield_coef_unc_kernel
             ff_host_coefficients(T, nw, ff_order, wsc.data(), c64);
@@ -159,11 +159,15 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
             ff_host_coefficients(T, nw, ff_order, wsc.data(), c64);
             double *d = s_wells.data() + ff_dummy_offset(nw);                                            // track_kernel's staging
             d[0] = 1e100; d[1] = 1.0; d[2] = 1.0;
-            fs.c64 = c64.data(); fs.c32 = nullptr; fs.off = T.off.data(); fs.cnt = T.cnt.data();
+            fs.c64 = c64.data(); fs.off = T.off.data(); fs.cnt = T.cnt.data();
         }
         for (int p = 0; p < P; ++p) {
             if (confined) {
-                if (use_ff) {
+                if (use_ff && ff_order == 16) {                                                          // launch_track's choice: the unrolled order
+                    if (mode == 0) dopri_track<true, 0, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
+                    else if (mode == 1) dopri_track<true, 1, true, 16>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
+                    else dopri_track<true, 2, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
+                } else if (use_ff) {
                     if (mode == 0) dopri_track<true, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                     else if (mode == 1) dopri_track<true, 1, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
                     else dopri_track<true, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);

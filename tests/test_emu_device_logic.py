@@ -65,15 +65,17 @@ def test_fused_tracker_and_rasteriser_bit_exact(golden, name):
     assert np.allclose(out["stats"]["bbox"], [v[:, 0].min(), v[:, 0].max(), v[:, 1].min(), v[:, 1].max()], rtol=1e-9)
 
 
-@pytest.mark.parametrize("tiles,shrink", [(64, 0.0), (9, 0.0), (16, 0.5)])
-def test_far_field_evaluation_in_the_tracker(golden, tiles, shrink):
+@pytest.mark.parametrize("tiles,shrink,order,eta", [(64, 0.0, 28, 0.3), (9, 0.0, 28, 0.3), (16, 0.5, 28, 0.3),
+                                                     (380, 0.0, 16, 0.15), (120, 0.3, 16, 0.15)])
+def test_far_field_evaluation_in_the_tracker(golden, tiles, shrink, order, eta):
     """field_feval_ff inside the tracker: same step sequence, same grid; shrink = 0.5 leaves three quarters of the
-    area to the direct-sum fallback."""
+    area to the direct-sum fallback.  (order 16, eta 0.15, ~380 tiles) is Engine's default since round 2 and runs the
+    UNROLLED evaluation (field_feval_ff<16>); the others run the loop."""
     g = golden("sto_perham.npz")
     s, spec, par = spec_of(g)
     gm = fixed_geom(g, s)
     ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
-    ff = ff_box(g, spec, tiles, shrink=shrink)
+    ff = ff_box(g, spec, tiles, order=order, eta=eta, shrink=shrink)
     direct = emu.capture(spec, par, ring, 2, max_verts=1024)
     far = emu.capture(spec, par, ring, 2, max_verts=1024, farfield=ff)
     assert np.array_equal(far["nverts"], direct["nverts"]) and np.array_equal(far["attempts"], direct["attempts"])
@@ -84,14 +86,15 @@ def test_far_field_evaluation_in_the_tracker(golden, tiles, shrink):
     assert np.array_equal(fused["counts"], g["fixed_counts"].astype(np.uint32))
 
 
-def test_far_field_200_wells_vs_executed_reference(golden):
+@pytest.mark.parametrize("tiles,order,eta", [(64, 28, 0.3), (380, 16, 0.15)])
+def test_far_field_200_wells_vs_executed_reference(golden, tiles, order, eta):
     """The synthetic 200-well field, traced by the EXECUTED reference (tests/golden/sto_wells200.npz): with the far field
     carrying ~195 of the 200 wells the tracker still reproduces every vertex and the fused pass every cell."""
     g = golden("sto_wells200.npz")
     s, spec, par = spec_of(g)
     gm = fixed_geom(g, s)
     ring = start_ring(s["xt"], s["yt"], s["rt"], s["P"])
-    ff = ff_box(g, spec, 64)
+    ff = ff_box(g, spec, tiles, order=order, eta=eta)
     out = emu.capture(spec, par, ring, 2, max_verts=1024, farfield=ff)
     worst = 0.0
     for p, t in enumerate(traces_of(g)):
@@ -109,7 +112,7 @@ def test_far_field_200_wells_vs_direct():
     direct = emu.capture(spec, par, ring, 0)
     bb = direct["stats"]["bbox"]
     gm = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(*bb)
-    ff = dict(farfield_grid((gm.xmin, gm.xmax, gm.ymin, gm.ymax), 64), order=28, eta=0.3)
+    ff = dict(farfield_grid((gm.xmin, gm.xmax, gm.ymin, gm.ymax), 380), order=16, eta=0.15)
     a = emu.capture(spec, par, ring, 1, geom=gm)
     b = emu.capture(spec, par, ring, 1, geom=gm, farfield=ff)
     assert a["stats"]["attempts"] == b["stats"]["attempts"] and np.array_equal(a["nverts"], b["nverts"])
@@ -146,22 +149,6 @@ def test_rasteriser_insert_fixture_and_random_tracks(golden):
         pf.register(1.0)
         assert (pf.nrows, pf.ncols) == (gm.nrows, gm.ncols)
         assert np.array_equal(counts, pf.pgrid.astype(np.uint32)), (dx, dy, umbra, step)
-
-
-@pytest.mark.parametrize("defines", ["-DONEKA_RK_LOOP=1 -DONEKA_FF_COEF_GLOBAL=1"])
-def test_prepared_build_knobs_keep_the_arithmetic(defines):
-    """The build knobs that are prepared but not yet timed on hardware (looped Runge-Kutta stages, far-field coefficients read
-    in place) must not change a single step: the whole module again, with the device code built that way."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("ONEKA_EMU_DEFINES"):
-        pytest.skip("already running under ONEKA_EMU_DEFINES")
-    env = dict(os.environ, ONEKA_EMU_DEFINES=defines)
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_device_logic.py"), "-x", "-q",
-                        "-k", "not prepared_build_knobs"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_dry_aquifer_and_attempt_guard(golden):

@@ -42,11 +42,18 @@ def _direct_ld(wxy, w, pts):
     return gx, gy, mag
 
 
+# (order, eta, tiles, bound on the error relative to sum |terms|): round 1's setting (truncation 3e-15 of a far term) and
+# Engine's default since round 2 (eta 0.15, order 16 -- the unrolled evaluation -- on ~380 tiles: truncation 8e-14 of a far
+# term, an order of magnitude below the 1e-12 of the Newton reciprocal in the direct-sum kernel)
+SETTINGS = [(28, 0.3, 64, 2e-14), (16, 0.15, 380, 1e-13)]
+
+
+@pytest.mark.parametrize("order,eta,tiles,bound", SETTINGS)
 @pytest.mark.parametrize("name,box", [("c4", (-600.0, 3400.0, -900.0, 900.0)), ("perham", (-1400.0, 1400.0, -1400.0, 1400.0)),
                                       ("long_prairie", (-800.0, 800.0, -800.0, 800.0))])
-def test_expansion_matches_direct_sum(name, box):
+def test_expansion_matches_direct_sum(name, box, order, eta, tiles, bound):
     wxy, w, xo, yo = _field(name)
-    grid = farfield_grid((xo + box[0], xo + box[1], yo + box[2], yo + box[3]), 64)
+    grid = farfield_grid((xo + box[0], xo + box[1], yo + box[2], yo + box[3]), tiles)
     rng = np.random.default_rng(1)
     n = 4000
     pts = np.stack([rng.uniform(grid["x0"], grid["x0"] + grid["ntx"] * grid["tile"], n),
@@ -57,19 +64,21 @@ def test_expansion_matches_direct_sum(name, box):
     pts = np.concatenate([pts, corners + 1e-9, corners - 1e-9])
     far_from_wells = np.min(np.hypot(pts[:, None, 0] - wxy[None, :, 0], pts[:, None, 1] - wxy[None, :, 1]), axis=1) > 0.5
     pts = pts[far_from_wells]
-    out, near = _eval(wxy, w, xo, yo, grid, 28, 0.3, pts)
+    out, near = _eval(wxy, w, xo, yo, grid, order, eta, pts)
     gx, gy, mag = _direct_ld(wxy, w, pts)
     err = np.maximum(np.abs(out[:, 0] - gx), np.abs(out[:, 1] - gy)).astype(np.float64) / mag
     inside = near >= 0
     assert inside.sum() > 3500
-    assert err.max() < 2e-14, err.max()                    # truncation 3e-15 of a far term + double rounding
+    print("%s order %d eta %.2f, %d tiles: max error %.2e of sum|terms|, mean near wells %.2f of %d"
+          % (name, order, eta, grid["ntx"] * grid["nty"], err.max(), near[inside].mean(), len(wxy)))
+    assert err.max() < bound, err.max()                    # truncation eta^order / (1 - eta) of a far term + double rounding
     assert np.all(near[inside] < len(wxy))
     if len(wxy) >= 29:
         assert near[inside].mean() < 0.45 * len(wxy)       # the point of it: most wells are in the polynomial
     # points outside the grid take the direct sum
     outside = np.array([[grid["x0"] - 5.0, grid["y0"] + 1.0], [grid["x0"] + grid["ntx"] * grid["tile"] + 1.0, grid["y0"] + 1.0],
                         [np.nan, 0.0]])
-    o2, n2 = _eval(wxy, w, xo, yo, grid, 28, 0.3, outside)
+    o2, n2 = _eval(wxy, w, xo, yo, grid, order, eta, outside)
     assert list(n2) == [-1, -1, -1]
     g2x, g2y, m2 = _direct_ld(wxy, w, outside[:2])
     assert np.all(np.abs(o2[:2, 0] - g2x).astype(float) <= 1e-14 * m2)

@@ -147,18 +147,31 @@ def test_c4_farfield_vs_direct_and_oracle(eng):
     check_subset(eng, spec, par, np.array([1, 4]), geom)          # oracle: equal vertex counts, endpoints, grid
 
 
-def test_farfield_off_for_small_fields_and_unconfined(eng, golden):
-    g = golden("sto_basic.npz")                                   # 2 wells
+def test_farfield_off_for_small_fields_and_on_request(eng, golden):
+    g = golden("sto_basic.npz")                                   # 2 wells: never
     s, spec, par = spec_of(g)
     gm = fixed_geom(g, s)
     eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
     assert eng.farfield_info() is None
-    g = golden("sto_perham.npz")
+    g = golden("sto_perham.npz")                                  # 29 wells, unconfined: on since round 2 (measured +11 % on B200) ...
     s, spec, par = spec_of(g)
     spec.confined = False
     gm = fixed_geom(g, s)
     eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    assert eng.farfield_info() is not None and eng.farfield_info()["order"] == 16
+    eng.farfield_unconfined = False                               # ... unless unconfined flow is taken out (ONEKA_FARFIELD_UNCONFINED=0)
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
     assert eng.farfield_info() is None
+    eng.farfield_unconfined = True
+    eng.farfield = "off"                                          # or the whole thing is (ONEKA_FARFIELD=off)
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    assert eng.farfield_info() is None
+    eng.farfield = "auto"
+    # the tile grid is sized to the shared-memory budget that keeps two tracking CTAs on an SM
+    spec.confined = True
+    eng.capture(spec, eng.upload(spec, par), gm, eng.new_counts(gm))
+    need = eng._ff_smem_info()
+    assert 0 < need["confined"] <= need["budget"] and eng.farfield_info()["ntx"] * eng.farfield_info()["nty"] > 64
 
 
 def test_unconfined_farfield_vs_direct(eng):
