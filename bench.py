@@ -447,8 +447,8 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
               "note": "cells registered = bits set in the per-realization bitmaps = sum of the count grid; word ops = one RED.OR per window row (x1.25 for rows straddling a word)"}
     if cx.red:
         raster["roofline"] = {"bound": "atomic (bit-set RED.OR to L2)", "achieved": raster["bitset_word_ops_per_s_estimate"] / 1e9,
-                              "peak": cx.red["l2_lane_private"], "unit": "1e9 word ops/s",
-                              "frac": raster["bitset_word_ops_per_s_estimate"] / 1e9 / cx.red["l2_lane_private"],
+                              "peak": cx.red["l2_lane_private"] * cx.world, "unit": "1e9 word ops/s (all GPUs)",
+                              "frac": raster["bitset_word_ops_per_s_estimate"] / 1e9 / (cx.red["l2_lane_private"] * cx.world),
                               "peaks": cx.red,
                               "reading": "the rasteriser is far from its atomic roofline: it is bound by the instructions that find each row's interval, "
                                          "not by the bit-set traffic (ncu: RED wavefronts 24 % of the L1 peak at C5)"}
