@@ -438,9 +438,9 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
     // near wells, two per trip (lists are padded to even length with the dummy well, whose term is ~1e-100)
     const unsigned int *po = fs.off + tile * ff.max_near;
-    const int n = fs.cnt[tile];
     const char *sw = reinterpret_cast<const char *>(s_wells);
     double hx = 0.0, hy = 0.0;                                   // second accumulator pair: two independent chains
+    const int n = fs.cnt[tile];
 #pragma unroll 1
     for (int i = 0; i < n; i += 2) {
         const uint2 o2 = *reinterpret_cast<const uint2 *>(po + i);
@@ -448,6 +448,8 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
         scaled_term(dx0, dy0, p0[0], p0[1], p0[2], gx, gy);
         scaled_term(dx0, dy0, p1[0], p1[1], p1[2], hx, hy);
     }
+    // (the odd well of a list on its own instead of the dummy padding: measured 14 % SLOWER, profiles/r02_knob_scan6.txt --
+    //  lanes of one warp in tiles of different parity then run the pair loop and the single-well tail one after the other)
     // far wells: the tile's polynomial
     double re, im;
     ff_poly_eval<ORD>(fs.c64 + tile * (ORD > 0 ? ORD : ff.order), ff.order, zr, zi, re, im);
@@ -691,24 +693,32 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     const bool edge_ok = k_edge < 0.125f;
     // (scan-line rows for every window width: measured 8 % faster than the node loop at 7-column windows (C3), 33 % at 15 (C5))
     const bool scan_ok = !all_exact && u > 0.0f;
+    // scan_ok folded into the two row thresholds: tested inside the loop, ptxas re-derived it PER ROW from the FP64 segment
+    // vector (5 FP64 instructions + DSETP of the len2 < 1e-20 test, i.e. 12 issue slots of a ~100-slot row)
+    const float skip_above = scan_ok ? u + tau : INFINITY;       // a row farther than this from the segment's y-extent cannot touch the capsule
+    const float scan_below = scan_ok ? u - tau : -INFINITY;      // a row nearer than this takes the scan-line path
 
     unsigned int *row = bm + (size_t)bottom * L.wpr;
     float fi = 0.0f;
     for (int i = bottom; i < top; ++i, row += L.wpr, fi += 1.0f) {
         const float cay = fmaf(fi, L.dy32, base_y);
         const float dmin = fmaxf(fmaxf(ylo - cay, cay - yhi), 0.0f);     // distance from the row to the segment's y-extent
-        if (scan_ok && dmin > u + tau) continue;                         // the row cannot touch the capsule
+        if (dmin > skip_above) continue;                                 // the row cannot touch the capsule
         bool done = false;
-        if (scan_ok && dmin < u - tau) {
+        if (dmin < scan_below) {
             const float tr = fmaf(cay, isy, kisy), tl = fmaf(cay, isy, -kisy);
             const float ha = sqrt_fast(fmaf(-cay, cay, u2));
             const float wb = cay - fbay;
             const float hb = sqrt_fast(fmaf(-wb, wb, u2));
             const bool ra = tr < 0.0f, rb = tr > 1.0f, la = tl < 0.0f, lb = tl > 1.0f;
-            const float xr = ra ? ha : (rb ? fbax + hb : fmaf(m, cay, cr));
-            const float xl = la ? -ha : (lb ? fbax - hb : fmaf(m, cay, -cr));
-            const bool caps_only = (la | lb) & (ra | rb);
-            if (xr > xl && (edge_ok | caps_only)) {                      // also false for nan
+            // (selects spelled out one by one: the nested conditional expressions became branches with BSSY / BSYNC pairs)
+            float xr = fmaf(m, cay, cr), xl = fmaf(m, cay, -cr);         // the straight edges ...
+            xr = rb ? fbax + hb : xr;                                    // ... cap b ...
+            xl = lb ? fbax - hb : xl;
+            xr = ra ? ha : xr;                                           // ... cap a
+            xl = la ? -ha : xl;
+            const bool cap_l = la | lb, cap_r = ra | rb;
+            if (xr > xl && (edge_ok | (cap_l & cap_r))) {                // also false for nan
                 const float fl = (xl - base_x) * L.inv_dx32, fr = (xr - base_x) * L.inv_dx32;
                 // round-to-nearest and float->int through the 1.5 * 2^23 trick (FMA-pipe adds instead of the
                 // quarter-rate FRND / F2I of the XU pipe); exact for |f| < 2^22, the window is far smaller
@@ -720,8 +730,9 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
                 int kl = il + (dl > 0.0f ? 1 : 0);                       // first node right of xl
                 int kr = ir - (dr > 0.0f ? 0 : 1);                       // last node left of xr
                 // is the node nearest to an end inside that end's error bound?
-                const bool amb_l = la ? (fabsf(dl) * ha < k_cap) : (lb ? (fabsf(dl) * hb < k_cap) : (fabsf(dl) < k_edge));
-                const bool amb_r = ra ? (fabsf(dr) * ha < k_cap) : (rb ? (fabsf(dr) * hb < k_cap) : (fabsf(dr) < k_edge));
+                const float hl = la ? ha : hb, hr = ra ? ha : hb;        // half-chord of the cap an end lies on (if it does)
+                const bool amb_l = cap_l ? (fabsf(dl) * hl < k_cap) : (fabsf(dl) < k_edge);
+                const bool amb_r = cap_r ? (fabsf(dr) * hr < k_cap) : (fabsf(dr) < k_edge);
                 if (amb_l | amb_r) {                                     // rare (~1e-4 of rows)
                     if (amb_l) { const int k = il; if (k >= 0 && k < ncol) kl = node_inside(rl, cay, i, left + k) ? k : k + 1; }
                     if (amb_r) { const int k = ir; if (k >= 0 && k < ncol) kr = node_inside(rr, cay, i, left + k) ? k : k - 1; }
@@ -738,6 +749,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
                         if (sh + span > 31) atomicOr(wp + 1, bits >> (32 - sh));
                     } else {
                         const int jb = left + kr;
+#pragma unroll 1
                         for (int w = ja >> 5; w <= (jb >> 5); ++w) {
                             const int lo = max(ja, w << 5), hi = min(jb, (w << 5) + 31);
                             atomicOr(row + w, (0xffffffffu >> (31 - (hi - lo))) << (lo & 31));
