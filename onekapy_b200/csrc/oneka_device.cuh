@@ -415,10 +415,15 @@ __host__ __device__ __forceinline__ bool ff_locate(int ntx, int nty, double gx0,
 }
 
 #if defined(__CUDACC__) || defined(ONEKA_EMU)
-// the direct sum as an out-of-line call: the rare particle outside the tile grid
-__device__ __noinline__ void field_direct_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
+// the direct sum as an out-of-line call: the rare particle outside the tile grid.  Results come back BY VALUE: reference
+// parameters of a real call are addresses, which put the six stage derivatives of the caller on the stack (2 STL.64 after and
+// 2 LDL.64 before every evaluation of the hot path, 34 local-memory instructions in the kernel).
+struct FieldValue { double fx, fy; int status; };
+__device__ __noinline__ FieldValue field_direct_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y)
 {
-    field_feval<true>(rc, s_wells, nw, x, y, fx, fy);
+    FieldValue v;
+    v.status = field_feval<true>(rc, s_wells, nw, x, y, v.fx, v.fy);
+    return v;
 }
 
 template <int ORD>
@@ -431,7 +436,8 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
     int tile;
     double zr, zi;
     if (!ff_locate(ff.ntx, ff.nty, ff.gx0, ff.gy0, ff.inv_tile, dx0, dy0, tile, zr, zi)) {
-        field_direct_cold(rc, s_wells, nw, x, y, fx, fy);
+        const FieldValue v = field_direct_cold(rc, s_wells, nw, x, y);
+        fx = v.fx; fy = v.fy;
         return PATH_OK;
     }
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
@@ -465,9 +471,11 @@ __device__ __forceinline__ int field_feval_ff(const RealConsts &rc, const double
 // comes from the SAME coefficients as the discharge (d/dz of the complex potential), so it costs one more Horner, in FP32.  Where
 // the screening value is within pot_err of k H^2/2 (or the point lies outside the tile grid) the whole evaluation is redone by the
 // direct-sum function, FP64 logs and all -- exactly what field_feval<false> does there.
-__device__ __noinline__ int field_direct_unc_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y, double &fx, double &fy)
+__device__ __noinline__ FieldValue field_direct_unc_cold(const RealConsts &rc, const double *s_wells, int nw, double x, double y)
 {
-    return field_feval<false>(rc, s_wells, nw, x, y, fx, fy);
+    FieldValue v;
+    v.status = field_feval<false>(rc, s_wells, nw, x, y, v.fx, v.fy);
+    return v;
 }
 
 __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
@@ -478,8 +486,11 @@ __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const do
     const double dy0 = y - rc.yo;
     int tile;
     double zr, zi;
-    if (!ff_locate(ff.ntx, ff.nty, ff.gx0, ff.gy0, ff.inv_tile, dx0, dy0, tile, zr, zi))
-        return field_direct_unc_cold(rc, s_wells, nw, x, y, fx, fy);
+    if (!ff_locate(ff.ntx, ff.nty, ff.gx0, ff.gy0, ff.inv_tile, dx0, dy0, tile, zr, zi)) {
+        const FieldValue v = field_direct_unc_cold(rc, s_wells, nw, x, y);
+        fx = v.fx; fy = v.fy;
+        return v.status;
+    }
     double gx = fma(rc.a2, dx0, fma(rc.c, dy0, rc.d));
     double gy = fma(rc.b2, dy0, fma(rc.c, dx0, rc.e));
     // near wells: discharge term + FP32 log term each (well_term, the unconfined store)
@@ -517,7 +528,9 @@ __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const do
         fy = gy * rc.inv_Hn;
         return PATH_OK;
     }
-    return field_direct_unc_cold(rc, s_wells, nw, x, y, fx, fy);
+    const FieldValue v = field_direct_unc_cold(rc, s_wells, nw, x, y);
+    fx = v.fx; fy = v.fy;
+    return v.status;
 }
 #endif
 
