@@ -587,13 +587,27 @@ def dropin_leg(cx, R, P, steps):
         pf = call()
         att += eng.last_stats["attempts"]
     secs = time.perf_counter() - t0
-    t1 = time.perf_counter()
+    # where a call's time goes: the three pieces of create_stochastic_capturezone timed one by one on the same problem
     from onekapy_b200.host.stochastic import sample_realizations
-    xt, yt = pb["wells"][pb["target"]][0:2]
-    sample_realizations(R, pb["base"], pb["c_dist"], pb["p_dist"], pb["t_dist"], pb["wells"], obs, xt, yt, rng=np.random.default_rng(1), log_rows=False)
+    from onekapy_b200.host.probabilityfield import ProbabilityField
+    from onekapy_b200.engine import FlowSpec
+    xt, yt, rt = pb["wells"][pb["target"]][0:3]
+    t1 = time.perf_counter()
+    params, _, _ = sample_realizations(R, pb["base"], pb["c_dist"], pb["p_dist"], pb["t_dist"], pb["wells"], obs, xt, yt, rng=np.random.default_rng(1), log_rows=False)
     host_s = time.perf_counter() - t1
+    spec = FlowSpec(well_xy=np.array([[w[0], w[1]] for w in pb["wells"]], dtype=float), xtarget=float(xt), ytarget=float(yt), rtarget=float(rt),
+                    npaths=P, duration=float(pb["duration"]), base=float(pb["base"]), spacing=float(pb["spacing"]), umbra=float(pb["umbra"]),
+                    confined=bool(pb["confined"]), tol=float(pb["tol"]), maxstep=float(pb["maxstep"]))
+    eng.run_exact(spec, params)
+    t2 = time.perf_counter()
+    res = eng.run_exact(spec, params)
+    eng_s = time.perf_counter() - t2
+    t3 = time.perf_counter()
+    ProbabilityField.from_counts(res["geom"], res["counts"], res["total_weight"])
+    fld_s = time.perf_counter() - t3
     return {"value": att / secs, "unit": "DOPRI5 attempts/s", "realizations_per_s": R * steps / secs, "ms_per_call": 1e3 * secs / steps, "steps": steps,
-            "host_sampling_ms_per_call": 1e3 * host_s, "grid": [int(pf.nrows), int(pf.ncols)], "total_weight": float(pf.total_weight),
+            "host_sampling_ms_per_call": 1e3 * host_s, "engine_run_exact_ms_per_call": 1e3 * eng_s, "probabilityfield_from_counts_ms": 1e3 * fld_s,
+            "grid": [int(pf.nrows), int(pf.ncols)], "total_weight": float(pf.total_weight),
             "affected_realizations": eng.last_stats.get("affected_realizations"),
             "api": "oneka.stochastic.create_stochastic_capturezone(target, npaths, duration, nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, "
                    "observations, spacing, umbra, confined, tol, maxstep) -> ProbabilityField: sample_realizations (host, one core) + Engine.run_exact + from_counts, wall clock"}
@@ -649,6 +663,14 @@ def run_ours(args):
         check = grid_check(cx, main["_state"], "c4" if wl == "c4full" else wl, per_rank_R or R, args.npaths or P, args.seed, args.unconfined,
                            recompute=list(range(world)) if wl != "c4full" else [world - 1])
 
+    # ---- the drop-in call itself (N = 1); before the CPU baseline: its OpenMP workers keep spinning on the host cores for a while ----
+    dropin = None
+    if world == 1 and wl == "c3" and not args.no_e2e and not args.unconfined:
+        try:
+            dropin = dropin_leg(cx, R, P, max(1, min(3, args.steps)))
+        except Exception as exc:
+            dropin = {"error": repr(exc)}
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -662,14 +684,6 @@ def run_ours(args):
                "python_reference_note": "the reference itself is pure Python and cannot run on this box (it is not in the repo); executed in the "
                                         "survey container it made 2.5 k attempts/s per core on perham and 5.6 k on basic (BASELINE.md section 2), "
                                         "~600x slower per core than this C port, which reproduces its traces bit for bit"}
-
-    # ---- the drop-in call itself (N = 1) ----
-    dropin = None
-    if world == 1 and wl == "c3" and not args.no_e2e and not args.unconfined:
-        try:
-            dropin = dropin_leg(cx, R, P, max(1, min(3, args.steps)))
-        except Exception as exc:
-            dropin = {"error": repr(exc)}
 
     # ---- the other configurations of BASELINE.json, short legs outside the headline's timed region ----
     legs = {}

@@ -44,7 +44,10 @@ static int fail(int code, const char *fmt, ...)
 //     for the realization's coefficient table, i.e. ~6x the tiles of the 128 x 6 shape at a lower order: C3 79.9 -> 64.6 ms,
 //     C4 33.1 -> 25.6 ms per step (profiles/r02_knob_scan2-4.txt).
 constexpr int TRACK_THREADS = 128, TRACK_MIN_CTAS = 6;
-constexpr int FF_THREADS = 256, FF_MIN_CTAS = 2;
+#ifndef ONEKA_FF_THREADS
+#define ONEKA_FF_THREADS 256
+#endif
+constexpr int FF_THREADS = ONEKA_FF_THREADS, FF_MIN_CTAS = 2;
 #ifndef ONEKA_FF_UNC_THREADS                 // unconfined far field: same shape (A/B knob while it is being measured)
 #define ONEKA_FF_UNC_THREADS 256
 #endif
