@@ -711,12 +711,11 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     const float skip_above = scan_ok ? u + tau : INFINITY;       // a row farther than this from the segment's y-extent cannot touch the capsule
     const float scan_below = scan_ok ? u - tau : -INFINITY;      // a row nearer than this takes the scan-line path
 
-    unsigned int *row = bm + (size_t)bottom * L.wpr;
-    float fi = 0.0f;
-    for (int i = bottom; i < top; ++i, row += L.wpr, fi += 1.0f) {
-        const float cay = fmaf(fi, L.dy32, base_y);
+    // THE GENERAL ROW (every case): skip test, scan-line interval with ambiguous ends settled node by node, spans wider than a
+    // word, and the node loop for near-tangent rows and rows the interval formulas do not cover.
+    auto general_row = [&](int i, float cay, unsigned int *row) {
         const float dmin = fmaxf(fmaxf(ylo - cay, cay - yhi), 0.0f);     // distance from the row to the segment's y-extent
-        if (dmin > skip_above) continue;                                 // the row cannot touch the capsule
+        if (dmin > skip_above) return;                                 // the row cannot touch the capsule
         bool done = false;
         if (dmin < scan_below) {
             const float tr = fmaf(cay, isy, kisy), tl = fmaf(cay, isy, -kisy);
@@ -772,7 +771,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
                 done = true;
             }
         }
-        if (done) continue;
+        if (done) return;
         // ---- node loop: columns in chunks of 32 starting at `left`; bit k of `mask` is column jc + k ----
         const float c1 = fbay * cay;
         for (int jc = left; jc < right; jc += 32) {
@@ -803,6 +802,54 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
                 atomicOr(wp, mask << sh);
                 if (sh && (mask >> (32 - sh))) atomicOr(wp + 1, mask >> (32 - sh));
             }
+        }
+    };
+
+    // Row loop.  Almost every row is the plain case -- inside the capsule's y-range, both interval ends unambiguous, at most 32
+    // nodes -- and is handled by a branch-light fast path: the same expressions as general_row evaluated unconditionally (all
+    // FP32; a nan only makes `fast` false), ONE test, then the one or two bit-set atomics.  Everything else re-runs the row
+    // through general_row.  (With the six tests of the general row in sequence the loop spent its time on branch resolution
+    // and reconvergence: ncu, profiles/r02_track_kernel_c3_stalls_by_region.txt.)
+    unsigned int *row = bm + (size_t)bottom * L.wpr;
+    float fi = 0.0f;
+    for (int i = bottom; i < top; ++i, row += L.wpr, fi += 1.0f) {
+        const float cay = fmaf(fi, L.dy32, base_y);
+        const float dmin = fmaxf(fmaxf(ylo - cay, cay - yhi), 0.0f);
+        const float tr = fmaf(cay, isy, kisy), tl = fmaf(cay, isy, -kisy);
+        const float ha = sqrt_fast(fmaf(-cay, cay, u2));
+        const float wb = cay - fbay;
+        const float hb = sqrt_fast(fmaf(-wb, wb, u2));
+        const bool ra = tr < 0.0f, rb = tr > 1.0f, la = tl < 0.0f, lb = tl > 1.0f;
+        float xr = fmaf(m, cay, cr), xl = fmaf(m, cay, -cr);
+        xr = rb ? fbax + hb : xr;
+        xl = lb ? fbax - hb : xl;
+        xr = ra ? ha : xr;
+        xl = la ? -ha : xl;
+        const bool cap_l = la | lb, cap_r = ra | rb;
+        const float fl = (xl - base_x) * L.inv_dx32, fr = (xr - base_x) * L.inv_dx32;
+        constexpr float MAGIC = 12582912.0f;
+        const float tl_m = fl + MAGIC, tr_m = fr + MAGIC;
+        const float rl = tl_m - MAGIC, rr = tr_m - MAGIC;
+        const int il = __float_as_int(tl_m) - 0x4B400000, ir = __float_as_int(tr_m) - 0x4B400000;
+        const float dl = fl - rl, dr = fr - rr;
+        const int kl = max(il + (dl > 0.0f ? 1 : 0), 0);                 // first node right of xl
+        const int kr = min(ir - (dr > 0.0f ? 0 : 1), ncol - 1);          // last node left of xr
+        const float hl = la ? ha : hb, hr = ra ? ha : hb;
+        const bool amb_l = cap_l ? (fabsf(dl) * hl < k_cap) : (fabsf(dl) < k_edge);
+        const bool amb_r = cap_r ? (fabsf(dr) * hr < k_cap) : (fabsf(dr) < k_edge);
+        const int span = kr - kl;
+        const bool fast = (dmin < scan_below) & (xr > xl) & (edge_ok | (cap_l & cap_r)) & !(amb_l | amb_r) & (span < 32);
+        if (fast) {
+            if (span >= 0) {
+                const int ja = left + kl;
+                unsigned int *wp = row + (ja >> 5);
+                const int sh = ja & 31;
+                const unsigned int bits = 0xffffffffu >> (31 - span);
+                atomicOr(wp, bits << sh);
+                if (sh + span > 31) atomicOr(wp + 1, bits >> (32 - sh));
+            }
+        } else {
+            general_row(i, cay, row);
         }
     }
 }
