@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: how profiles/r02_knob_scan*.txt were produced.  The -D macros of the variants (ONEKA_TRACK_THREADS, FUSED_MIN_CTAS,
+# ONEKA_FF_ORDER_FIXED, ONEKA_FF_PREFETCH, ONEKA_FF_NEAR_TAIL ...) existed only while the scan ran; the winners are now the code.
 # round 2, second scan: CTA size x tile count x order x eta of the far field (and the Horner loop unrolled at a fixed order).
 # The variants are built here by tools/build_variant.sh; every line is a short bench run (C3 R=4000, C4 R=1024).
 set -u

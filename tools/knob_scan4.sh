@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: how profiles/r02_knob_scan*.txt were produced.  The -D macros of the variants (ONEKA_TRACK_THREADS, FUSED_MIN_CTAS,
+# ONEKA_FF_ORDER_FIXED, ONEKA_FF_PREFETCH, ONEKA_FF_NEAR_TAIL ...) existed only while the scan ran; the winners are now the code.
 # round 2, fourth scan: 256 threads x 2 CTAs per SM (128 registers, 113 KB of shared memory per CTA): tiles / order / eta; + one ncu capture
 set -u
 mkdir -p gpurun_out

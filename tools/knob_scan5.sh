@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: how profiles/r02_knob_scan*.txt were produced.  The -D macros of the variants (ONEKA_TRACK_THREADS, FUSED_MIN_CTAS,
+# ONEKA_FF_ORDER_FIXED, ONEKA_FF_PREFETCH, ONEKA_FF_NEAR_TAIL ...) existed only while the scan ran; the winners are now the code.
 # round 2, fifth scan: CTA shape / register budget on the kernels WITHOUT the far field (direct sums, unconfined, raster-heavy C5, tiny C1)
 set -u
 mkdir -p gpurun_out
