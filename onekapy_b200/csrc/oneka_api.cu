@@ -43,15 +43,9 @@ static int fail(int code, const char *fmt, ...)
 //   far field: 256 threads, 2 CTAs per SM -- 128 registers (no spills; 80 cost 200 B of them) and up to ~112 KB of shared memory
 //     for the realization's coefficient table, i.e. ~6x the tiles of the 128 x 6 shape at a lower order: C3 79.9 -> 64.6 ms,
 //     C4 33.1 -> 25.6 ms per step (profiles/r02_knob_scan2-4.txt).
-constexpr int TRACK_THREADS = 128, TRACK_MIN_CTAS = 6;
-#ifndef ONEKA_FF_THREADS
-#define ONEKA_FF_THREADS 256
-#endif
-constexpr int FF_THREADS = ONEKA_FF_THREADS, FF_MIN_CTAS = 2;
-#ifndef ONEKA_FF_UNC_THREADS                 // unconfined far field: same shape (A/B knob while it is being measured)
-#define ONEKA_FF_UNC_THREADS 256
-#endif
-constexpr int FF_UNC_THREADS = ONEKA_FF_UNC_THREADS, FF_UNC_MIN_CTAS = 768 / ONEKA_FF_UNC_THREADS == 3 ? 2 : 768 / ONEKA_FF_UNC_THREADS;
+constexpr int TRACK_THREADS = 128, TRACK_MIN_CTAS = 6;      // (5 and 4 CTAs per SM, no spills: within 1.5 % on C5 / C1 / direct C3 / C4, re-measured in round 2)
+constexpr int FF_THREADS = 256, FF_MIN_CTAS = 2;
+constexpr int FF_UNC_THREADS = 256, FF_UNC_MIN_CTAS = 2;     // unconfined far field: the same shape (128 x 6 measured 2x slower, scan 6)
 constexpr int FF_ORDER_UNROLLED = 16;        // the order whose Horner loop is unrolled at compile time (Engine's default)
 constexpr int N_STATS = 16;
 
