@@ -166,44 +166,51 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
 // coalesced (k is the fastest index) and every 16-byte P load feeds COEF_RB complex FMAs from registers, the scaled
 // discharges of the realization block are broadcast from shared memory.  (Round 1 had one warp per (realization, tile):
 // every P element re-read from L2 for every realization -- 28 GB per 10 000 realizations at 378 tiles, 3.3 ms of a 158 ms step.)
-constexpr int COEF_RB = 8, COEF_THREADS = 128;
+constexpr int COEF_RB = 8, COEF_THREADS = 128, COEF_WCHUNK = 512;    // wells staged per pass: 8 x 512 doubles = 32 KB
 
 template <bool CONFINED>
 __global__ void __launch_bounds__(COEF_THREADS)
 farfield_coef_kernel(int nw, int ntiles, int order, long long nr, const double2 *__restrict__ P, const double *__restrict__ q,
                      const double *__restrict__ poro, const double *__restrict__ thick, double2 *__restrict__ out)
 {
-    extern __shared__ double s_w[];                              // [COEF_RB][nw]
+    __shared__ double s_w[COEF_RB * COEF_WCHUNK];                // [COEF_RB][wells of this pass]
     const long long r0 = (long long)blockIdx.y * COEF_RB;
     const int nb = (int)min((long long)COEF_RB, nr - r0);
-    for (int i = threadIdx.x; i < COEF_RB * nw; i += COEF_THREADS) {
-        const int j = i / nw, w = i - j * nw;
-        double v = 0.0;
-        if (j < nb) {
-            const long long r = r0 + j;
-            const double scale = CONFINED ? 1.0 / (thick[r] * poro[r]) : 1.0;
-            v = q[(size_t)r * nw + w] * 0.15915494309189535 * scale;
-        }
-        s_w[i] = v;
-    }
-    __syncthreads();
     const int e = blockIdx.x * COEF_THREADS + threadIdx.x;       // entry (tile, k)
-    if (e >= ntiles * order) return;
-    const int t = e / order, k = e - t * order;
+    const bool live = e < ntiles * order;
+    const int t = live ? e / order : 0, k = live ? e - t * order : 0;
     const double2 *Pt = P + (size_t)t * nw * order + k;
     double ar[COEF_RB], ai[COEF_RB];
 #pragma unroll
     for (int j = 0; j < COEF_RB; ++j) { ar[j] = 0.0; ai[j] = 0.0; }
+    for (int w0 = 0; w0 < nw; w0 += COEF_WCHUNK) {               // (one pass for fields of up to 512 wells)
+        const int wn = min(COEF_WCHUNK, nw - w0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < COEF_RB * wn; i += COEF_THREADS) {
+            const int j = i / wn, w = i - j * wn;
+            double v = 0.0;
+            if (j < nb) {
+                const long long r = r0 + j;
+                const double scale = CONFINED ? 1.0 / (thick[r] * poro[r]) : 1.0;
+                v = q[(size_t)r * nw + w0 + w] * 0.15915494309189535 * scale;
+            }
+            s_w[j * COEF_WCHUNK + w] = v;
+        }
+        __syncthreads();
+        if (live) {
 #pragma unroll 2
-    for (int w = 0; w < nw; ++w) {
-        const double2 pk = __ldg(Pt + (size_t)w * order);
+            for (int w = 0; w < wn; ++w) {
+                const double2 pk = __ldg(Pt + (size_t)(w0 + w) * order);
 #pragma unroll
-        for (int j = 0; j < COEF_RB; ++j) {
-            const double ww = s_w[j * nw + w];
-            ar[j] = fma(ww, pk.x, ar[j]);
-            ai[j] = fma(ww, pk.y, ai[j]);
+                for (int j = 0; j < COEF_RB; ++j) {
+                    const double ww = s_w[j * COEF_WCHUNK + w];
+                    ar[j] = fma(ww, pk.x, ar[j]);
+                    ai[j] = fma(ww, pk.y, ai[j]);
+                }
+            }
         }
     }
+    if (!live) return;
 #pragma unroll
     for (int j = 0; j < COEF_RB; ++j)
         if (j < nb) out[((size_t)(r0 + j) * ntiles + t) * order + k] = make_double2(ar[j], ai[j]);
@@ -608,8 +615,7 @@ static int prepare_farfield(oneka_ctx *ctx, const oneka_model_desc *m, long long
     const long long nby = (nr + COEF_RB - 1) / COEF_RB;
     if (nby > 65535) return fail(ONEKA_ERR_ARG, "too many realizations in one far-field launch (%lld)", nr);
     const dim3 cgrid((unsigned)((ntiles * f.order + COEF_THREADS - 1) / COEF_THREADS), (unsigned)nby);
-    const size_t csmem = (size_t)COEF_RB * f.nw * sizeof(double);
-    if (csmem > 48 * 1024) return fail(ONEKA_ERR_ARG, "far field: nw = %d wells exceed the coefficient kernel's staging", f.nw);
+    const size_t csmem = 0;                                          // (static shared memory: COEF_RB x COEF_WCHUNK doubles)
     ff_check_wells_kernel<<<1, 128, 0, ctx->stream>>>(f.nw, f.wells, well_xy_dev, ctx->stats_dev);
     if (m->confined) {
         farfield_coef_kernel<true><<<cgrid, COEF_THREADS, csmem, ctx->stream>>>(f.nw, ntiles, f.order, nr, f.P, q, poro, thick, ctx->ff.coef);

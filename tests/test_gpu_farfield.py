@@ -119,9 +119,11 @@ def test_particles_outside_the_tile_grid_take_the_direct_sum(eng, golden):
     out = eng.trace(spec, dp, max_verts=1024)
     assert np.array_equal(out["nverts"].ravel(), [len(t) for t in traces_of(g)])
     # fused: the engine would rebuild the tables for the lattice; call the C ABI's state as it is by keeping the key
-    eng._ff_key = (eng._ff_wells_key(spec), tuple(float(v) for v in (gm.xmin, gm.xmax, gm.ymin, gm.ymax)))
+    eng._ff_key = (eng._ff_wells_key(spec), tuple(float(v) for v in (gm.xmin, gm.xmax, gm.ymin, gm.ymax)), eng._ff_settings())
+    ntiles_before = eng.farfield_info()["ntx"] * eng.farfield_info()["nty"]
     counts = eng.new_counts(gm)
     eng.capture(spec, dp, gm, counts)
+    assert eng.farfield_info()["ntx"] * eng.farfield_info()["nty"] == ntiles_before <= 16      # the quarter-area tables were kept
     assert np.array_equal(counts.cpu().numpy().view(np.uint32), g["fixed_counts"].astype(np.uint32))
 
 

@@ -434,6 +434,13 @@ def test_run_with_subsampled_pilot(eng, golden):
     eng._geom_hint[tuple(spec.duration if i == 4 else v for i, v in enumerate(key_dur))] = (small, None)
     f = eng.run(spec, par)
     assert f["stats"]["rerun_realizations"] > 0 and f["geom"] == a["geom"] and np.array_equal(f["counts"], a["counts"])
+    # ... ONCE: the estimate that proved too small is replaced by a larger one, the next call fits
+    f2 = eng.run(spec, par)
+    assert f2["stats"]["rerun_realizations"] == 0 and np.array_equal(f2["counts"], a["counts"])
+    # and the cache of estimates is a small LRU, not an ever-growing dict
+    for k in range(20):
+        eng._hint_put(("dummy", k), (small, None))
+    assert len(eng._geom_hint) <= 8 and ("dummy", 19) in eng._geom_hint
     for r in (b, c):
         assert r["geom"] == a["geom"] and np.array_equal(r["counts"], a["counts"])
 

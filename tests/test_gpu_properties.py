@@ -195,6 +195,44 @@ def test_three_hundred_wells(eng):
     check_subset(eng, spec, par, np.array([0, 3]), geom)
 
 
+def test_nine_hundred_wells_coefficients_in_passes(eng):
+    """900 wells: the far-field coefficient GEMM stages the discharges in passes of 512 wells (farfield_coef_kernel), the well
+    store takes 25 KB of the CTA's shared-memory budget.  Far field == direct sums (steps, grid) and == the oracle, confined
+    and unconfined."""
+    from onekapy_b200 import synthetic
+    from onekapy_b200.engine import FlowSpec
+    pb = synthetic.well_field(900, seed=11)
+    par = synthetic.sample_rows_fast(pb, 3, 5)
+    xt, yt, rt = pb["wells"][pb["target"]][0:3]
+    for confined in (True, False):
+        spec = FlowSpec(well_xy=np.array([[w[0], w[1]] for w in pb["wells"]], dtype=float), xtarget=float(xt), ytarget=float(yt),
+                        rtarget=float(rt), npaths=96, duration=float(pb["duration"]), base=float(pb["base"]), spacing=float(pb["spacing"]),
+                        umbra=float(pb["umbra"]), confined=confined, tol=float(pb["tol"]), maxstep=float(pb["maxstep"]))
+        dp = eng.upload(spec, par)
+        eng.farfield = "off"
+        geom, st0 = lattice_for(eng, spec, dp)
+        a = eng.new_counts(geom)
+        eng.reset_stats()
+        eng.capture(spec, dp, geom, a)
+        sa = eng.read_stats()
+        assert eng.farfield_info() is None
+        eng.farfield = "auto"
+        b = eng.new_counts(geom)
+        eng.reset_stats()
+        eng.capture(spec, dp, geom, b)
+        sb = eng.read_stats()
+        info = eng.farfield_info()
+        assert info is not None and info["mean_near"] < 40
+        need = eng._ff_smem_info()
+        assert need["confined" if confined else "unconfined"] <= need["budget"]
+        assert sa["attempts"] == sb["attempts"] and sa["steps"] == sb["steps"] and sb["n_not_ok"] == sa["n_not_ok"]
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+        print("900 wells confined=%s: %d x %d tiles, mean near %.1f; far field == direct sums (%d attempts)"
+              % (confined, info["ntx"], info["nty"], info["mean_near"], sb["attempts"]))
+        if confined:
+            check_subset(eng, spec, par, np.array([1]), geom)
+
+
 def test_many_contexts_on_one_device(eng):
     """15 live contexts on one device give the same grid (each owns its stream-ordered workspace)."""
     from onekapy_b200.engine import Engine
