@@ -339,8 +339,43 @@ def parity_block(cx, spec, params, geom, n, seed=5):
             "oracle_seconds": t, "against": "oracle/ (C restatement pinned bit for bit to the executed reference, tests/golden) on the same rows and lattice"}
 
 
+def postprocess_block(cx, counts, total_weight, sigma=2.0, reps=3):
+    """SURVEY N3 on the leg's own count grid, device-resident, CUDA events: the exceedance histogram behind create_impact_plot
+    (oneka/visualize.py:382-386 sorts the whole grid) and the separable FP64 Gaussian of create_probability_plot (:228-233)."""
+    import ctypes as C
+    from onekapy_b200 import _cabi
+    from onekapy_b200.host.postprocess import gaussian_taps
+    torch, eng = cx.torch, cx.eng
+    nrows, ncols = int(counts.shape[0]), int(counts.shape[1])
+    ncell = nrows * ncols
+    nbins = int(total_weight) + 1
+    hist = torch.zeros(max(nbins, 2), dtype=torch.int64, device=cx.dev)
+    tmp = torch.empty((nrows, ncols), dtype=torch.float64, device=cx.dev)
+    out = torch.empty_like(tmp)
+    w, lw = gaussian_taps(sigma)
+    s = torch.cuda.current_stream(cx.dev)
+
+    def timed(fn):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        for _ in range(reps):
+            fn()
+        b.record(s)
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+    h_ms = timed(lambda: _cabi.check(eng._L.oneka_count_histogram(eng._h, counts.data_ptr(), ncell, max(nbins, 2), hist.data_ptr())))
+    g_ms = timed(lambda: _cabi.check(eng._L.oneka_gaussian_smooth(eng._h, counts.data_ptr(), nrows, ncols, float(total_weight), w.ctypes.data,
+                                                                   int(lw), tmp.data_ptr(), out.data_ptr())))
+    captured = int(ncell - int(hist[0].item()))
+    return {"cells": ncell, "count_histogram_ms": h_ms, "count_histogram_GBps": 4.0 * ncell / (h_ms * 1e-3) / 1e9,
+            "gaussian_smooth_ms": g_ms, "gaussian_smooth_GBps": 28.0 * ncell / (g_ms * 1e-3) / 1e9, "sigma_nodes": sigma, "taps": 2 * lw + 1,
+            "cells_captured_at_least_once": captured,
+            "note": "algorithmic bytes: histogram 4 B per cell; smooth 4 B read + 8 B written (rows), 8 B read + 8 B written (columns) = 28 B per cell"}
+
+
 def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined=False, full_pilot=False, e2e_steps=0,
-            parity_n=0, sampler=None, scaling="weak", total=None, exact_e2e=False, note=None):
+            parity_n=0, sampler=None, scaling="weak", total=None, exact_e2e=False, note=None, postprocess=False):
     """One timed leg: K steps on rows resident in HBM (device-timed, max over ranks) + optional e2e / parity."""
     torch, eng = cx.torch, cx.eng
     from onekapy_b200.engine import RealizationParams, start_ring
@@ -433,6 +468,12 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
     rst = eng.read_stats()
     ragg = cx.gather([float(fresh.sum(dtype=torch.int64).item()), float(rst["steps"]), float(rst["exact_tests"])]).sum(axis=0)
     cells_step, segs_step, exact_step = (float(v) for v in ragg)
+    post = None
+    if postprocess:                                          # N3 on this rank's grid of one step (counts <= R)
+        try:
+            post = postprocess_block(cx, fresh, R)
+        except Exception as exc:
+            post = {"error": repr(exc)}
     del fresh
     step_s = ms_max * 1e-3 / steps
     # window of insert() (probabilityfield.py:298-301) for a segment of the mean accepted length: rows x columns tested by the
@@ -463,7 +504,7 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
     nominal = 148 * 64 * 2 * (cx.max_mhz or 1965) * 1e6 / 1e12
     # DRAM traffic of the fused kernel from the ncu --set full capture in profiles/ (bytes per 1000 realizations of the
     # perham field, dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch: the path is not HBM-bound
-    traffic = (75.1e6 if ff_info else 27.9e6) * (R / 1000.0) if wl == "c3" and not unconfined else None
+    traffic = (137.0e6 if ff_info else 27.9e6) * (R / 1000.0) if wl == "c3" and not unconfined else None
     # with the far-field compression the kernel EXECUTES fewer flops than the reference's formulation needs: per evaluation
     # 20 (regional) + 16 per near well + 8 per polynomial term + ~16 of tile lookup, FMA = 2 (estimate from the mean near count)
     if ff_info:
@@ -473,7 +514,9 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
     roofline = {"bound": "fp64", "kernel": "track_kernel<%s, raster%s>" % ("unconfined" if unconfined else "confined", ", far field" if ff_info else ""),
                 "achieved": achieved, "peak": probe_tf,
                 "unit": "TFLOP/s", "frac": achieved / probe_tf, "frac_of_nominal": achieved / nominal, "peak_nominal": nominal, "traffic": traffic,
-                "traffic_note": "bytes per launch scaled from profiles/r01_track_kernel%s_raw.csv (ncu --set full at R=1000); HBM is idle (< 0.1 %% of peak), the bound is the FP64 pipe / issue port" % ("_farfield" if ff_info else ""),
+                "traffic_note": "bytes per launch scaled from %s (ncu --set full at R=1000: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic input is (Nw+9)*8 B per realization; "
+                                "the rest is the realization's far-field coefficient table (97 KB, written once by the coefficient GEMM, read once by its four CTAs) and the registration bitmaps; "
+                                "HBM is idle (< 0.2 %% of peak), the bound is the issue port / FP64 pipe" % ("profiles/r02_track_kernel_c3_raw.csv" if ff_info else "profiles/r01_track_kernel_raw.csv"),
                 "peak_source": "in-run DFMA probe (oneka_fp64_probe); MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x max clock = %.1f" % nominal,
                 "flops_per_attempt": flops_per_attempt(nw), "attempts_per_launch": att_per_launch, "kernel_ms_per_launch": track_ms,
                 "flops_executed_per_attempt_estimate": exec_flops, "frac_executed_estimate": achieved * exec_flops / flops_per_attempt(nw) / probe_tf,
@@ -490,6 +533,8 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
            "roofline": roofline, "raster": raster, "breakdown": breakdown, "gpu_launches": int(per_rank[:, 9].sum())}
     if note:
         out["note"] = note
+    if post is not None:
+        out["postprocess"] = post
 
     # ---- e2e: the public calls with host buffers, every step ----
     if e2e_steps > 0:
@@ -701,7 +746,7 @@ def run_ours(args):
                 r = run_leg(cx, leg, "c4", 1024, 0, 2, 3, args.seed, farfield="off", full_pilot=True, parity_n=1,
                             note="the same 200-well field with the far-field compression off: the reference's own formulation (direct sum over all wells)")
             elif leg == "c5":
-                r = run_leg(cx, leg, "c5", 2048, 0, 3, 3, args.seed, full_pilot=True, e2e_steps=2, parity_n=1)
+                r = run_leg(cx, leg, "c5", 2048, 0, 3, 3, args.seed, full_pilot=True, e2e_steps=2, parity_n=1, postprocess=True)
             elif leg == "c1":
                 r = run_leg(cx, leg, "c1", 100, 100, 5, 3, args.seed, full_pilot=True, e2e_steps=3, parity_n=8, exact_e2e=True,
                             note="the reference's CPU-sized configuration: 10 000 particles on 148 SMs, launch-latency bound (~1 % of the FP64 peak by construction)")

@@ -62,6 +62,9 @@ struct oneka_ctx {
     // host-buffer staging (oneka_capture_host), grow-only
     void *stage = nullptr;
     size_t stage_bytes = 0;
+    // small scratch of the auxiliary entry points (Gaussian taps, point evaluation, distancesquared), grow-only
+    void *aux = nullptr;
+    size_t aux_bytes = 0;
     // far-field compression (oneka_set_farfield): tile geometry, static tables, per-launch coefficient workspace
     struct FarField {
         bool on = false;
@@ -419,19 +422,36 @@ fp64_probe_kernel(int iters, double seed, double *sink)
     if (s == 12345.678) sink[0] = s;     // never true; keeps the chains alive
 }
 
-// exceedance histogram of the count grid (visualize.py:382-386 is a sort of integer-valued data)
+// exceedance histogram of the count grid (visualize.py:382-386 is a sort of integer-valued data).  Bins live in shared memory
+// while they fit (SMEM = true: nbins <= HIST_SMEM_BINS; shared-memory atomics run at ~5e12 word operations/s, oneka_red_probe, where
+// all CTAs hammering the same few global bins ran at 48 GB/s of input on the 23 M-cell C5 grid); zeros -- most nodes -- are
+// counted in a register and added once per warp.
+constexpr int HIST_SMEM_BINS = 12288;
+template <bool SMEM>
 __global__ void __launch_bounds__(256)
 count_histogram_kernel(const unsigned int *counts, long long ncell, int nbins, unsigned long long *hist)
 {
+    extern __shared__ unsigned int s_hist[];
+    if (SMEM) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_hist[b] = 0u;
+        __syncthreads();
+    }
     unsigned long long zeros = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) {
         const unsigned int c = counts[i];
         if (c == 0) { ++zeros; continue; }                          // most nodes: aggregate per warp below
-        atomicAdd(hist + min(c, (unsigned int)(nbins - 1)), 1ULL);
+        const unsigned int b = min(c, (unsigned int)(nbins - 1));
+        if (SMEM) atomicAdd(s_hist + b, 1u);
+        else atomicAdd(hist + b, 1ULL);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) zeros += __shfl_down_sync(0xffffffffu, zeros, o);
     if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(hist, zeros);
+    if (SMEM) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            if (s_hist[b]) atomicAdd(hist + b, (unsigned long long)s_hist[b]);
+    }
 }
 
 // one axis of scipy.ndimage.gaussian_filter(mode='constant', cval=0): out = sum_k w[k] in[.. + k - lw ..]
@@ -510,6 +530,17 @@ static TrackParams make_track(const oneka_model_desc *m, const double *well_xy_d
 
 // the well store of oneka_device.cuh (blocks of 4 wells, WELL_BLK doubles each) + 16 bytes of slack
 static size_t track_smem(int nw) { return (size_t)well_store_doubles(nw) * sizeof(double) + 256; }   // slack: the loops load the first well of the block after the last
+
+static int ensure_aux(oneka_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->aux_bytes) return ONEKA_OK;
+    if (ctx->aux) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFree(ctx->aux)); ctx->aux = nullptr; ctx->aux_bytes = 0; }
+    const size_t want = bytes < 65536 ? 65536 : bytes;
+    cudaError_t e = cudaMalloc(&ctx->aux, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ONEKA_ERR_NOMEM, "cudaMalloc(%zu) for scratch failed: %s", want, cudaGetErrorString(e)); }
+    ctx->aux_bytes = want;
+    return ONEKA_OK;
+}
 
 static int ensure_bitmaps(oneka_ctx *ctx, size_t bytes)
 {
@@ -785,6 +816,7 @@ void oneka_destroy(oneka_ctx *ctx)
     for (auto &ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     if (ctx->bitmaps) cudaFree(ctx->bitmaps);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->stats_dev) cudaFree(ctx->stats_dev);
     if (ctx->ff.P) cudaFree(ctx->ff.P);
     if (ctx->ff.near_off) cudaFree(ctx->ff.near_off);
@@ -1004,12 +1036,12 @@ int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const doub
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int nw = m->nw;
     const size_t nd = (size_t)3 * nw + 3 + 6 + 2 * (size_t)npts + 8 * (size_t)npts;
-    double *buf = nullptr;
-    CUDA_TRY(cudaMalloc(&buf, nd * sizeof(double)));
+    int rc = ensure_aux(ctx, nd * sizeof(double));
+    if (rc) return rc;
+    double *buf = (double *)ctx->aux;
     double *d_wxy = buf, *d_q = d_wxy + 2 * nw, *d_k = d_q + nw, *d_n = d_k + 1, *d_H = d_n + 1, *d_cf = d_H + 1;
     double *d_pts = d_cf + 6, *d_out = d_pts + 2 * npts;
     cudaStream_t s = ctx->stream;
-    int rc = ONEKA_OK;
     do {
 #define TRY2(expr) if ((expr) != cudaSuccess) { rc = fail(ONEKA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); break; }
         if (nw) { TRY2(cudaMemcpyAsync(d_wxy, well_xy_host, 2 * nw * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1031,7 +1063,6 @@ int oneka_eval_points_host(oneka_ctx *ctx, const oneka_model_desc *m, const doub
         TRY2(cudaStreamSynchronize(s));
 #undef TRY2
     } while (0);
-    cudaFree(buf);
     return rc;
 }
 
@@ -1271,7 +1302,10 @@ int oneka_count_histogram(oneka_ctx *ctx, const uint32_t *counts_dev, int64_t nc
     long long blocks = (ncell + 255) / 256;
     const long long cap = (long long)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    count_histogram_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(counts_dev, ncell, nbins, (unsigned long long *)hist_dev);
+    if (nbins <= HIST_SMEM_BINS)
+        count_histogram_kernel<true><<<(unsigned)blocks, 256, (size_t)nbins * sizeof(unsigned int), ctx->stream>>>(counts_dev, ncell, nbins, (unsigned long long *)hist_dev);
+    else
+        count_histogram_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(counts_dev, ncell, nbins, (unsigned long long *)hist_dev);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return ONEKA_OK;
@@ -1283,20 +1317,17 @@ int oneka_gaussian_smooth(oneka_ctx *ctx, const uint32_t *counts_dev, int32_t nr
     if (!ctx || !counts_dev || !w_host || !tmp_dev || !out_dev || nrows <= 0 || ncols <= 0 || lw < 0 || !(total_weight > 0.0))
         return fail(ONEKA_ERR_ARG, "bad argument to oneka_gaussian_smooth");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    double *w_dev = nullptr;
     const size_t wb = (size_t)(2 * lw + 1) * sizeof(double);
-    CUDA_TRY(cudaMalloc(&w_dev, wb));
-    cudaError_t e = cudaMemcpyAsync(w_dev, w_host, wb, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        const dim3 grid((ncols + 255) / 256, nrows);
-        gaussian_axis_kernel<0, true><<<grid, 256, 0, ctx->stream>>>(counts_dev, nullptr, 1.0 / total_weight, nrows, ncols, w_dev, lw, tmp_dev);
-        gaussian_axis_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(nullptr, tmp_dev, 1.0, nrows, ncols, w_dev, lw, out_dev);
-        ctx->launches += 2;
-        e = cudaGetLastError();
-    }
-    cudaStreamSynchronize(ctx->stream);      // w_host / w_dev lifetime
-    cudaFree(w_dev);
-    if (e != cudaSuccess) return fail(ONEKA_ERR_CUDA, "gaussian smooth failed: %s", cudaGetErrorString(e));
+    int rc = ensure_aux(ctx, wb);                                   // context-owned scratch: no allocation, no synchronisation per call
+    if (rc) return rc;
+    double *w_dev = (double *)ctx->aux;
+    // (a pageable host source is staged by the driver before cudaMemcpyAsync returns: w_host may be released by the caller at once)
+    CUDA_TRY(cudaMemcpyAsync(w_dev, w_host, wb, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 grid((ncols + 255) / 256, nrows);
+    gaussian_axis_kernel<0, true><<<grid, 256, 0, ctx->stream>>>(counts_dev, nullptr, 1.0 / total_weight, nrows, ncols, w_dev, lw, tmp_dev);
+    gaussian_axis_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(nullptr, tmp_dev, 1.0, nrows, ncols, w_dev, lw, out_dev);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
     return ONEKA_OK;
 }
 
@@ -1399,8 +1430,9 @@ int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host
     if (!ctx || n < 0 || (n && (!abc_host || !out_host))) return fail(ONEKA_ERR_ARG, "bad argument to oneka_distancesquared_host");
     if (n == 0) return ONEKA_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    double *buf = nullptr;
-    CUDA_TRY(cudaMalloc(&buf, (size_t)n * 7 * sizeof(double)));
+    int rc = ensure_aux(ctx, (size_t)n * 7 * sizeof(double));
+    if (rc) return rc;
+    double *buf = (double *)ctx->aux;
     cudaStream_t s = ctx->stream;
     cudaError_t e = cudaMemcpyAsync(buf, abc_host, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
@@ -1410,7 +1442,6 @@ int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf + 6 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(buf);
     if (e != cudaSuccess) return fail(ONEKA_ERR_CUDA, "oneka_distancesquared_host failed: %s", cudaGetErrorString(e));
     return ONEKA_OK;
 }

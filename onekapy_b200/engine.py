@@ -632,22 +632,8 @@ class Engine:
 
         tick = _PhaseTimer(self.torch, self.device)
         # ---- 1. lattice estimate ----
-        self.reset_stats()
         if hint is None:
-            if R > 0:
-                rstep = max(1, R // max(1, pilot))
-                pstep = max(1, spec.npaths // max(1, pilot_paths))
-                if rstep == 1 and pstep == 1:
-                    self.capture(spec, dp)
-                else:
-                    self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
-            bbox = parallel.union_bbox(parallel.gather_rows(self.read_stats()["bbox"], group, dev))
-            if not np.all(np.isfinite(bbox)):
-                raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
-            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
-            pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
-            work = base.expanded(bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
-            ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
+            work, ff_box, _ = self._pilot_lattice(spec, params, dp, start, base, group, dev, pilot, pilot_paths, margin)
         else:
             work, ff_box = hint
             if work.deltax != base.deltax or work.deltay != base.deltay:
@@ -724,6 +710,35 @@ class Engine:
             self._hint_put(key, (keep, ff_box))
         self.last_stats = stats
         return dict(counts=out, geom=final, total_weight=float(total), stats=stats, per_path=pp, work_geom=work)
+
+    def _pilot_lattice(self, spec, params, dp, start, base, group, dev, pilot, pilot_paths, margin):
+        """Lattice estimate shared by run() and run_exact(): a tracking-only pass over <= `pilot` realizations (evenly strided)
+        x ~`pilot_paths` paths (evenly strided around the ring) -> bounding box, agreed over the ranks by ONE packed all-gather
+        -> `base` expanded to the box plus `margin` of its size on every side, and the box + 10 % for the far-field tiles
+        (the lattice's safety margin would make the tiles 1.5x larger and their near lists twice as long).
+        Returns (geom, ff_box, total realizations over all ranks); geom is None when there are no realizations anywhere."""
+        from . import parallel
+        R = len(params)
+        self.reset_stats()
+        if R > 0:
+            rstep = max(1, R // max(1, pilot))
+            pstep = max(1, spec.npaths // max(1, pilot_paths))
+            if rstep == 1 and pstep == 1:
+                self.capture(spec, dp)
+            else:
+                self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
+        g = parallel.gather_rows(list(self.read_stats()["bbox"]) + [R], group, dev)
+        total = int(g[:, 4].sum())
+        if total == 0:
+            return None, None, 0
+        bbox = parallel.union_bbox(g[:, :4])
+        if not np.all(np.isfinite(bbox)):
+            raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
+        w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
+        pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
+        geom = base.expanded(bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
+        ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
+        return geom, ff_box, total
 
     # -- lattice hints: a small LRU keyed by the problem (ADVICE r1: bounded, and replaced when it proved too small) ----
     @staticmethod
@@ -811,29 +826,13 @@ class Engine:
         #    makes a poor estimate cost a partial re-run, never a wrong grid)
         key = self._problem_key(spec)
         hint = self._hint_get(key) if reuse_lattice else None          # every rank makes the same calls, so the caches agree
-        self.reset_stats()
         if hint is not None:
             geom, ff_box = hint
         else:
-            if R > 0:
-                rstep = max(1, R // max(1, pilot))
-                pstep = max(1, spec.npaths // max(1, pilot_paths))
-                if rstep == 1 and pstep == 1:
-                    self.capture(spec, dp)
-                else:
-                    self.capture(spec, self.upload(spec, params.slice(0, R, rstep), start[::pstep]))
-            g1 = parallel.gather_rows(list(self.read_stats()["bbox"]) + [R], group, dev)
-            if int(g1[:, 4].sum()) == 0:
+            base = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget)
+            geom, ff_box, total = self._pilot_lattice(spec, params, dp, start, base, group, dev, pilot, pilot_paths, margin)
+            if geom is None:
                 return self._empty_result(spec)          # no realizations anywhere: the fresh 3 x 3 field (stochastic.py:212)
-            bbox = parallel.union_bbox(g1[:, :4])
-            if not np.all(np.isfinite(bbox)):
-                raise OnekaError("pilot pass produced a non-finite bounding box %r" % (bbox,))
-            w, h = bbox[1] - bbox[0], bbox[3] - bbox[2]
-            pw, ph = margin * max(w, spec.umbra), margin * max(h, spec.umbra)
-            geom = LatticeGeom.anchored(spec.spacing, spec.spacing, spec.xtarget, spec.ytarget).expanded(
-                bbox[0] - pw, bbox[1] + pw, bbox[2] - ph, bbox[3] + ph)
-            # far-field tiles cover where the particles are (pilot box + 10 %), not the lattice's safety margin
-            ff_box = (bbox[0] - 0.1 * w, bbox[1] + 0.1 * w, bbox[2] - 0.1 * h, bbox[3] + 0.1 * h)
         # 2./3. guarded capture on the estimated lattice: realizations that run off it are flagged and not registered
         work_geom = geom
         counts = self.new_counts(geom)
