@@ -55,22 +55,49 @@ def _legacy_rows(dists, nrows):
             raise DistributionError('<arg> must be a scalar, pair, or triple.')
     if not rnd or nrows == 0:
         return out
-    U = np.random.random_sample((nrows, len(rnd)))
-    for c, j in enumerate(rnd):
-        d = dists[j]
-        u = U[:, c]
-        if len(d) == 2:
-            out[:, j] = d[0] + (d[1] - d[0]) * u
+    # Uniform columns together, triangular columns together (per-column parameters broadcast along the rows), in row blocks
+    # that stay in cache with the temporaries reused: the same elementwise operations in the same order as the scalar
+    # formulas and the same row-major consumption of the stream, so the values are bit-identical.  (A Python loop over 200
+    # strided columns of 16 MB arrays cost 130 ms per 10 000 realizations of the 200-well field, most of the sampling.)
+    m = len(rnd)
+    cu = np.array([c for c, j in enumerate(rnd) if len(dists[j]) == 2], dtype=np.intp)
+    ct = np.array([c for c, j in enumerate(rnd) if len(dists[j]) == 3], dtype=np.intp)
+    lo_u = np.array([float(dists[rnd[c]][0]) for c in cu])
+    hi_u = np.array([float(dists[rnd[c]][1]) for c in cu])
+    left = np.array([float(dists[rnd[c]][0]) for c in ct])
+    mode = np.array([float(dists[rnd[c]][1]) for c in ct])
+    right = np.array([float(dists[rnd[c]][2]) for c in ct])
+    base = right - left
+    leftbase = mode - left
+    ratio = leftbase / base
+    leftprod = leftbase * base
+    rightprod = (right - mode) * base
+    contiguous = rnd == list(range(rnd[0], rnd[0] + m))
+    all_tri = len(ct) == m
+    BLK = max(1, 262144 // m)                                 # ~2 MB of doubles per temporary
+    for r0 in range(0, nrows, BLK):
+        r1 = min(nrows, r0 + BLK)
+        U = np.random.random_sample((r1 - r0, m))
+        V = U if all_tri else np.empty_like(U)
+        if len(cu):
+            V[:, cu] = lo_u + (hi_u - lo_u) * U[:, cu]       # np.random.uniform: lo + (hi - lo) U
+        if len(ct):
+            u = U if all_tri else U[:, ct]
+            lo = np.sqrt(u * leftprod)
+            lo += left                                        # left + sqrt(U leftprod)
+            hi = np.subtract(1.0, u)
+            hi *= rightprod
+            np.sqrt(hi, out=hi)
+            np.subtract(right, hi, out=hi)                    # right - sqrt((1 - U) rightprod)
+            res = np.where(u <= ratio, lo, hi)
+            if all_tri:
+                V = res
+            else:
+                V[:, ct] = res
+        if contiguous:
+            out[r0:r1, rnd[0]:rnd[0] + m] = V
         else:
-            left, mode, right = (float(t) for t in d)
-            base = right - left
-            leftbase = mode - left
-            ratio = leftbase / base
-            leftprod = leftbase * base
-            rightprod = (right - mode) * base
-            lo = left + np.sqrt(u * leftprod)
-            hi = right - np.sqrt((1.0 - u) * rightprod)
-            out[:, j] = np.where(u <= ratio, lo, hi)
+            out[r0:r1, rnd] = V
     return out
 
 
