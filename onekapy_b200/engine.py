@@ -80,6 +80,13 @@ class RealizationParams:
         s = slice(r0, r1, step)
         return RealizationParams(self.q[s], self.cond[s], self.poro[s], self.thick[s], self.coef[s])
 
+    @staticmethod
+    def concat(chunks):
+        chunks = list(chunks)
+        return RealizationParams(q=np.concatenate([c.q for c in chunks]), cond=np.concatenate([c.cond for c in chunks]),
+                                 poro=np.concatenate([c.poro for c in chunks]), thick=np.concatenate([c.thick for c in chunks]),
+                                 coef=np.concatenate([c.coef for c in chunks]))
+
 
 @functools.lru_cache(maxsize=16)
 def _start_ring_cached(xtarget, ytarget, rtarget, npaths):
@@ -112,7 +119,7 @@ def _ptr(t):
 class DeviceParams:
     """RealizationParams resident in HBM (torch tensors own the memory)."""
 
-    def __init__(self, torch, device, params: RealizationParams, well_xy, start_xy):
+    def __init__(self, torch, device, params: RealizationParams, well_xy, start_xy, like=None):
         f64 = torch.float64
         self.R = len(params)
         self.q = torch.as_tensor(params.q, dtype=f64).to(device)
@@ -120,8 +127,23 @@ class DeviceParams:
         self.poro = torch.as_tensor(params.poro, dtype=f64).to(device)
         self.thick = torch.as_tensor(params.thick, dtype=f64).to(device)
         self.coef = torch.as_tensor(params.coef, dtype=f64).to(device)
-        self.well_xy = torch.as_tensor(np.ascontiguousarray(well_xy, dtype=np.float64)).to(device)
-        self.start_xy = torch.as_tensor(np.array(start_xy, dtype=np.float64, order="C", copy=True)).to(device)   # the cached ring is read-only
+        if like is not None:                               # a further chunk of the same run: wells and start ring are shared
+            self.well_xy, self.start_xy = like.well_xy, like.start_xy
+        else:
+            self.well_xy = torch.as_tensor(np.ascontiguousarray(well_xy, dtype=np.float64)).to(device)
+            self.start_xy = torch.as_tensor(np.array(start_xy, dtype=np.float64, order="C", copy=True)).to(device)   # the cached ring is read-only
+
+    @staticmethod
+    def concat(torch, chunks):
+        """Chunks of one run (same wells, same start ring) as one DeviceParams (device-side concatenation)."""
+        if len(chunks) == 1:
+            return chunks[0]
+        out = object.__new__(DeviceParams)
+        out.R = sum(c.R for c in chunks)
+        for name in ("q", "cond", "poro", "thick", "coef"):
+            setattr(out, name, torch.cat([getattr(c, name) for c in chunks], dim=0).contiguous())
+        out.well_xy, out.start_xy = chunks[0].well_xy, chunks[0].start_xy
+        return out
 
     def select(self, idx):
         """The rows `idx` (int64 device tensor) as a new DeviceParams sharing wells and start ring."""
@@ -413,12 +435,26 @@ class Engine:
         return out
 
     # -- uploads ----------------------------------------------------------------------------
-    def upload(self, spec: FlowSpec, params: RealizationParams, start_xy=None) -> DeviceParams:
+    def upload(self, spec: FlowSpec, params: RealizationParams, start_xy=None, like=None) -> DeviceParams:
         if start_xy is None:
             start_xy = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
         if params.q.shape[1] != len(spec.well_xy):
             raise ValueError("q has %d columns but the spec has %d wells" % (params.q.shape[1], len(spec.well_xy)))
-        return DeviceParams(self.torch, self.device, params, spec.well_xy, start_xy)
+        return DeviceParams(self.torch, self.device, params, spec.well_xy, start_xy, like=like)
+
+    def _upload_overlapped(self, spec, params, like):
+        """Upload a further chunk on a side stream, so that the copy (a blocking one: the rows are pageable host memory)
+        does not queue behind the kernels of the previous chunk; the compute stream then waits for the copy."""
+        torch = self.torch
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = self._stream
+        with torch.cuda.stream(self._copy_stream):
+            dp = self.upload(spec, params, like=like)
+        main.wait_stream(self._copy_stream)
+        for name in ("q", "cond", "poro", "thick", "coef"):
+            getattr(dp, name).record_stream(main)
+        return dp
 
     # -- compute_backtrace with stored vertices (oneka/capturezone.py:127-253) ------------------
     def trace(self, spec: FlowSpec, dp: DeviceParams, max_verts=4096):
@@ -562,8 +598,8 @@ class Engine:
         from .lattice import clip_windows
         return clip_windows(self.torch, base, final, bb, prior)
 
-    def run_exact(self, spec: FlowSpec, params: RealizationParams, group=None, per_path=False, base: Optional[LatticeGeom] = None,
-                  pilot=256, margin=0.25, pilot_paths=128, reuse_lattice=True, two_pass_below=16):
+    def run_exact(self, spec: FlowSpec, params, group=None, per_path=False, base: Optional[LatticeGeom] = None,
+                  pilot=256, margin=0.25, pilot_paths=128, reuse_lattice=True, two_pass_below=16, total=None):
         """Like run(), but reproduces the reference's order-dependent clipping exactly (the drop-in default).
 
         The reference inserts path n into the grid as expanded to the union of the bounding boxes of paths 0..n, in
@@ -582,12 +618,26 @@ class Engine:
         Cost: one fused pass + 2x the affected fraction (~1 % at 10 000 realizations) instead of a tracking pass before the
         fused one.  With fewer than `two_pass_below` realizations most of them are affected and the two-pass scheme
         (oneka_path_bboxes, then oneka_capture_clipped for everything) is cheaper; it is also what compute_capturezone uses.
-        `base`: the grid before the first path (default: fresh 3 x 3 on the target, stochastic.py:212)."""
+        `base`: the grid before the first path (default: fresh 3 x 3 on the target, stochastic.py:212).
+        `params` may also be an ITERABLE of RealizationParams chunks with `total` = their realization count (this rank's):
+        the chunks are consumed one fused launch at a time, so a generator that samples and fits the next chunk on the
+        host (host.stochastic) runs while the GPU tracks the current one -- the drop-in call hides its host part that way."""
         from . import parallel
         from .lattice import clip_windows, clip_windows_rows, realization_boxes, union_before, affected_realizations
         torch = self.torch
-        R, P = len(params), int(spec.npaths)
+        P = int(spec.npaths)
         start = start_ring(spec.xtarget, spec.ytarget, spec.rtarget, spec.npaths)
+        later = iter(())
+        if not isinstance(params, RealizationParams):
+            if total is None:
+                raise ValueError("run_exact(chunks): `total` (the number of realizations in the chunks) is required")
+            later = iter(params)
+            params = next(later, None)
+            if params is None or int(total) < two_pass_below:      # nothing, or a small run: no point in streaming
+                params = RealizationParams.concat(([params] if params is not None else []) + list(later)) if params is not None \
+                    else RealizationParams(q=np.zeros((0, len(spec.well_xy))), cond=[], poro=[], thick=[], coef=np.zeros((0, 6)))
+                later = iter(())
+        R = int(total) if total is not None else len(params)
         dp = self.upload(spec, params, start)
         dev = self.device if group is not None else None
         rank = 0
@@ -647,7 +697,22 @@ class Engine:
         flags = torch.zeros(R, dtype=torch.int32, device=self.device)
         bb = torch.empty((R, P, 4), dtype=torch.float64, device=self.device)
         self.reset_stats()
-        pp = self.capture(spec, dp, work, counts, per_path=per_path, flags=flags, ff_box=ff_box, bbox_out=bb) if R else None
+        pp, dps, done = None, [], 0
+        chunk_dp = dp
+        while chunk_dp is not None and chunk_dp.R:
+            if done + chunk_dp.R > R:
+                raise ValueError("run_exact(chunks): the chunks hold more than total = %d realizations" % R)
+            one = self.capture(spec, chunk_dp, work, counts, per_path=per_path, flags=flags[done:done + chunk_dp.R], ff_box=ff_box,
+                               bbox_out=bb[done:done + chunk_dp.R])          # asynchronous: the host goes on to the next chunk
+            if per_path:
+                pp = one if pp is None else {k: torch.cat([pp[k], one[k]], dim=0) for k in one}
+            dps.append(chunk_dp)
+            done += chunk_dp.R
+            nxt = next(later, None)                                          # (a generator samples / fits the next chunk here)
+            chunk_dp = self._upload_overlapped(spec, nxt, dp) if nxt is not None else None
+        if done != R:
+            raise ValueError("run_exact(chunks): total = %d but the chunks hold %d realizations" % (R, done))
+        dp = DeviceParams.concat(torch, dps) if dps else dp
         stats = self.read_stats()
 
         tick('fused_pass')

@@ -115,19 +115,19 @@ def _mvn_rows(rng, ev, factor):
 SAMPLE_CHUNK = 32768          # realizations per host batch: bounds WA [chunk, nobs, 6] (160 MB at 100 observations)
 
 
-def sample_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, observations,
-                        xtarget, ytarget, rng=None, fit_method="auto", log_rows=True):
-    """Steps (1)-(4) of oneka/stochastic.py:186-199 for all realizations -> RealizationParams.
+def iter_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, observations,
+                      xtarget, ytarget, rng=None, fit_method="auto", log_rows=True, chunk=SAMPLE_CHUNK):
+    """Steps (1)-(4) of oneka/stochastic.py:186-199, `chunk` realizations at a time: yields (RealizationParams, ev, cov).
 
-    Vectorised over realizations, yet the rows are the ones the reference's loop would produce: the
-    discharges / conductivity / porosity / thickness consume np.random's global state in the
-    reference's order (`_legacy_rows`), and A..F come from `rng.multivariate_normal` row by row
-    (`_mvn_rows`) -- the reference builds a fresh unseeded default_rng() per realization (:241), so
-    without `rng` one unseeded Generator serves all rows; pass a seeded one for reproducible rows.
+    Vectorised over the realizations of a chunk, yet the rows are the ones the reference's loop would produce: the
+    discharges / conductivity / porosity / thickness consume np.random's global state in the reference's order
+    (`_legacy_rows`: realization by realization, so chunks concatenate to the same stream), and A..F come from
+    `rng.multivariate_normal` row by row (`_mvn_rows`; likewise sequential) -- the reference builds a fresh unseeded
+    default_rng() per realization (:241), so without `rng` one unseeded Generator serves all rows; pass a seeded one for
+    reproducible rows.  The two streams are independent, so interleaving them chunk by chunk changes nothing.
 
-    fit_method: "lstsq" = the reference's LAPACK calls per realization; "qr" = one stacked
-    factorisation (same estimator, rounding differs at ~1e-9 relative); "auto" = lstsq up to 4096
-    realizations, qr above."""
+    fit_method: "lstsq" = the reference's LAPACK calls per realization; "qr" = one stacked factorisation (same estimator,
+    rounding differs at ~1e-9 relative); "auto" = lstsq up to 4096 realizations IN TOTAL, qr above."""
     nw = len(stochastic_wells)
     R = int(nrealizations)
     dists = [w[3] for w in stochastic_wells] + [c_dist, p_dist, t_dist]
@@ -136,29 +136,35 @@ def sample_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_
     if fit_method == "auto":
         fit_method = "lstsq" if R <= 4096 else "qr"
     g = rng if rng is not None else np.random.default_rng()
-    q = np.zeros((R, nw))
-    k = np.zeros(R)
-    n = np.zeros(R)
-    H = np.zeros(R)
-    coef = np.zeros((R, 6))
-    ev = np.zeros((R, 6))
-    cov = np.zeros((R, 6, 6))
-    # all legacy variates first (their stream is independent of the Generator's), then fit + draw chunk by chunk
-    for r0 in range(0, R, SAMPLE_CHUNK):
-        r1 = min(R, r0 + SAMPLE_CHUNK)
+    chunk = max(1, int(chunk))
+    for r0 in range(0, R, chunk):
+        r1 = min(R, r0 + chunk)
         rows = _legacy_rows(dists, r1 - r0)
-        q[r0:r1], k[r0:r1], n[r0:r1], H[r0:r1] = rows[:, :nw], rows[:, nw], rows[:, nw + 1], rows[:, nw + 2]
-    for r0 in range(0, R, SAMPLE_CHUNK):
-        r1 = min(R, r0 + SAMPLE_CHUNK)
-        ev[r0:r1], cov[r0:r1], fac = fit_batch(obs, xtarget, ytarget, base, wxy, q[r0:r1], k[r0:r1], H[r0:r1],
-                                               method=fit_method, with_factor=True)
-        coef[r0:r1] = _mvn_rows(g, ev[r0:r1], fac)
-    if log_rows and log.isEnabledFor(logging.INFO):
-        for i in range(R):
-            recharge = 2 * (coef[i, 0] + coef[i, 1])
-            log.info('Realization #{0:d}: {1:.2f}, {2:.2f}, {3:.2f}, {4:.2f}, {5:.4e}'
-                     .format(i, base, k[i], n[i], H[i], recharge))
-    return RealizationParams(q=q, cond=k, poro=n, thick=H, coef=coef), ev, cov
+        q, k, n, H = np.ascontiguousarray(rows[:, :nw]), rows[:, nw].copy(), rows[:, nw + 1].copy(), rows[:, nw + 2].copy()
+        ev, cov, fac = fit_batch(obs, xtarget, ytarget, base, wxy, q, k, H, method=fit_method, with_factor=True)
+        coef = _mvn_rows(g, ev, fac)
+        if log_rows and log.isEnabledFor(logging.INFO):
+            for i in range(r1 - r0):
+                recharge = 2 * (coef[i, 0] + coef[i, 1])
+                log.info('Realization #{0:d}: {1:.2f}, {2:.2f}, {3:.2f}, {4:.2f}, {5:.4e}'
+                         .format(r0 + i, base, k[i], n[i], H[i], recharge))
+        yield RealizationParams(q=q, cond=k, poro=n, thick=H, coef=coef), ev, cov
+
+
+def sample_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, observations,
+                        xtarget, ytarget, rng=None, fit_method="auto", log_rows=True):
+    """All realizations at once -> (RealizationParams, ev [R, 6], cov [R, 6, 6]); see iter_realizations."""
+    parts = list(iter_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells, observations, xtarget, ytarget,
+                                   rng=rng, fit_method=fit_method, log_rows=log_rows))
+    if not parts:
+        nw = len(stochastic_wells)
+        return RealizationParams(q=np.zeros((0, nw)), cond=np.zeros(0), poro=np.zeros(0), thick=np.zeros(0), coef=np.zeros((0, 6))), \
+            np.zeros((0, 6)), np.zeros((0, 6, 6))
+    return RealizationParams.concat([p for p, _, _ in parts]), np.concatenate([e for _, e, _ in parts]), np.concatenate([c for _, _, c in parts])
+
+
+import os as _os
+STREAM_CHUNK = int(_os.environ.get("ONEKA_STREAM_CHUNK", "2048"))   # realizations per chunk when the drop-in call overlaps its host part with the GPU (~30 ms of GPU work at C3)
 
 
 def create_stochastic_capturezone(
@@ -171,16 +177,24 @@ def create_stochastic_capturezone(
     Returns a ProbabilityField whose pgrid holds, per node, the number of realizations whose
     capture zone covers it, and total_weight = nrealizations."""
     xtarget, ytarget, rtarget = stochastic_wells[target][0:3]
-    params, _, _ = sample_realizations(nrealizations, base, c_dist, p_dist, t_dist, stochastic_wells,
-                                       observations, xtarget, ytarget, rng=rng)
     spec = FlowSpec(well_xy=np.array([[w[0], w[1]] for w in stochastic_wells], dtype=float).reshape(-1, 2),
                     xtarget=float(xtarget), ytarget=float(ytarget), rtarget=float(rtarget), npaths=int(npaths),
                     duration=float(duration), base=float(base), spacing=float(spacing), umbra=float(umbra),
                     confined=bool(confined), tol=float(tol), maxstep=float(maxstep))
     eng = engine if engine is not None else default_engine()
-    # exact_clip=True reproduces the reference's auto-expanding grid cell for cell (one extra tracking pass);
-    # False rasterises on the final lattice directly (a superset differing in ~1e-3 of the cells, see DESIGN.md)
-    res = eng.run_exact(spec, params) if exact_clip else eng.run(spec, params)
+    R = int(nrealizations)
+    # exact_clip=True reproduces the reference's auto-expanding grid cell for cell (ONE fused pass + a fix-up of the few
+    # realizations the growing grid clipped); False rasterises on the final lattice directly (a superset differing in
+    # ~1e-3 of the cells, see DESIGN.md)
+    if exact_clip and R >= 2 * STREAM_CHUNK:
+        # sampling and fit of chunk k + 1 run on the host while the GPU tracks chunk k (Engine.run_exact consumes the
+        # generator one fused launch at a time); the rows are the ones one monolithic sampling would produce
+        chunks = (p for p, _, _ in iter_realizations(R, base, c_dist, p_dist, t_dist, stochastic_wells, observations, xtarget, ytarget,
+                                                     rng=rng, chunk=STREAM_CHUNK))
+        res = eng.run_exact(spec, chunks, total=R)
+    else:
+        params, _, _ = sample_realizations(R, base, c_dist, p_dist, t_dist, stochastic_wells, observations, xtarget, ytarget, rng=rng)
+        res = eng.run_exact(spec, params) if exact_clip else eng.run(spec, params)
     if res["stats"]["n_not_ok"]:
         log.warning(' %d trace(s) terminated prematurely before duration.', res["stats"]["n_not_ok"])
     return ProbabilityField.from_counts(res["geom"], res["counts"], res["total_weight"])

@@ -373,7 +373,7 @@ def test_run_vs_auto_expanding_reference(eng, golden, name):
     assert frac < 2e-2
 
 
-@pytest.mark.parametrize("scheme", ["two_pass", "one_pass", "one_pass_tight_lattice", "one_pass_hint"])
+@pytest.mark.parametrize("scheme", ["two_pass", "one_pass", "one_pass_tight_lattice", "one_pass_hint", "one_pass_chunks", "small_run_chunks"])
 @pytest.mark.parametrize("name", CAPTURES)
 def test_run_exact_equals_auto_expanding_reference(eng, golden, name, scheme):
     """Engine.run_exact reproduces the reference's order-dependent clipping: the grid of the executed reference,
@@ -391,6 +391,20 @@ def test_run_exact_equals_auto_expanding_reference(eng, golden, name, scheme):
         assert 1 <= res["stats"]["affected_realizations"] <= len(par) and res["stats"]["rerun_realizations"] == 0
     elif scheme == "one_pass_tight_lattice":
         res = eng.run_exact(spec, par, two_pass_below=0, reuse_lattice=False, pilot=1, pilot_paths=2, margin=0.0)
+    elif scheme == "one_pass_chunks":
+        # the rows arrive as a generator of chunks (what the drop-in call does to overlap host sampling with the GPU): one
+        # fused launch per chunk into the same grid, the lattice estimated from the first chunk alone
+        gen = (par.slice(r, min(len(par), r + 2)) for r in range(0, len(par), 2))
+        res = eng.run_exact(spec, gen, total=len(par), two_pass_below=0, reuse_lattice=False, per_path=True)
+        whole = eng.run_exact(spec, par, two_pass_below=0, reuse_lattice=False, per_path=True)
+        assert np.array_equal(res["counts"], whole["counts"]) and res["stats"]["attempts"] == whole["stats"]["attempts"]
+        for k in ("end_xy", "nverts", "status"):
+            assert np.array_equal(res["per_path"][k], whole["per_path"][k])
+    elif scheme == "small_run_chunks":
+        gen = (par.slice(r, r + 1) for r in range(len(par)))
+        res = eng.run_exact(spec, gen, total=len(par), two_pass_below=10**9)       # materialised, two passes
+        with pytest.raises(ValueError):
+            eng.run_exact(spec, (par.slice(r, r + 1) for r in range(len(par))), total=len(par) + 1, two_pass_below=0)
     else:
         eng.run_exact(spec, par, two_pass_below=0)
         n0 = eng.launch_count()

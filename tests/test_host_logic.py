@@ -295,3 +295,27 @@ def test_empty_realization_params():
     assert len(p) == 0 and p.q.shape == (0, 29) and p.coef.shape == (0, 6)
     full = RealizationParams(q=np.ones((4, 3)), cond=np.ones(4), poro=np.ones(4), thick=np.ones(4), coef=np.ones((4, 6)))
     assert full.slice(2, 2).q.shape == (0, 3) and full.slice(1, 4, 2).q.shape == (2, 3)
+
+
+def test_chunked_sampling_concatenates_to_the_monolithic_rows():
+    """host.stochastic.iter_realizations (what the drop-in call streams to the GPU chunk by chunk) draws the rows one monolithic
+    sample_realizations would: both RNG streams are consumed realization by realization."""
+    from onekapy_b200 import problems
+    from onekapy_b200.host.stochastic import iter_realizations, sample_realizations
+    from onekapy_b200.host.utilities import filter_obs
+    pb = problems.load("perham")
+    obs = filter_obs(pb["observations"], pb["wells"], pb["buffer"])
+    xt, yt = pb["wells"][pb["target"]][0:2]
+    args = (pb["base"], pb["c_dist"], pb["p_dist"], pb["t_dist"], pb["wells"], obs, xt, yt)
+    for method in ("lstsq", "qr"):
+        np.random.seed(77)
+        whole, ev, cov = sample_realizations(200, *args, rng=np.random.default_rng(5), fit_method=method, log_rows=False)
+        np.random.seed(77)
+        parts = list(iter_realizations(200, *args, rng=np.random.default_rng(5), fit_method=method, log_rows=False, chunk=37))
+        assert [len(p) for p, _, _ in parts] == [37] * 5 + [15]
+        for name in ("q", "cond", "poro", "thick"):
+            assert np.array_equal(np.concatenate([getattr(p, name) for p, _, _ in parts]), getattr(whole, name)), name
+        coef = np.concatenate([p.coef for p, _, _ in parts])
+        scale = np.abs(whole.coef).max(axis=0)
+        assert np.all(np.abs(coef - whole.coef) <= 1e-9 * scale), (method, np.abs(coef - whole.coef).max(axis=0) / scale)
+        assert np.allclose(np.concatenate([e for _, e, _ in parts]), ev, rtol=1e-9, atol=0)
