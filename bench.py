@@ -628,8 +628,11 @@ def dropin_leg(cx, R, P, steps):
     cx.torch.cuda.synchronize(cx.dev)
     t0 = time.perf_counter()
     att = 0
+    each = []
     for _ in range(steps):
+        tc = time.perf_counter()
         pf = call()
+        each.append(round(1e3 * (time.perf_counter() - tc), 2))
         att += eng.last_stats["attempts"]
     secs = time.perf_counter() - t0
     # where a call's time goes: the three pieces of create_stochastic_capturezone timed one by one on the same problem
@@ -650,7 +653,7 @@ def dropin_leg(cx, R, P, steps):
     t3 = time.perf_counter()
     ProbabilityField.from_counts(res["geom"], res["counts"], res["total_weight"])
     fld_s = time.perf_counter() - t3
-    return {"value": att / secs, "unit": "DOPRI5 attempts/s", "realizations_per_s": R * steps / secs, "ms_per_call": 1e3 * secs / steps, "steps": steps,
+    return {"value": att / secs, "unit": "DOPRI5 attempts/s", "realizations_per_s": R * steps / secs, "ms_per_call": 1e3 * secs / steps, "ms_each_call": each, "steps": steps,
             "host_sampling_ms_per_call": 1e3 * host_s, "engine_run_exact_ms_per_call": 1e3 * eng_s, "probabilityfield_from_counts_ms": 1e3 * fld_s,
             "grid": [int(pf.nrows), int(pf.ncols)], "total_weight": float(pf.total_weight),
             "affected_realizations": eng.last_stats.get("affected_realizations"),
@@ -712,7 +715,7 @@ def run_ours(args):
     dropin = None
     if world == 1 and wl == "c3" and not args.no_e2e and not args.unconfined:
         try:
-            dropin = dropin_leg(cx, R, P, max(1, min(3, args.steps)))
+            dropin = dropin_leg(cx, R, P, max(1, min(5, args.steps)))
         except Exception as exc:
             dropin = {"error": repr(exc)}
 
