@@ -89,6 +89,12 @@ def make_workload(name, realizations, npaths, seed, unconfined=False):
         label = "C5 basic field on a fine lattice (spacing 4, umbra 20: ~15x15-node windows, 4096^2-class grid), %d realizations x %d paths per GPU per step" % (R, P)
     else:
         raise SystemExit("unknown workload %r" % name)
+    if make_workload.umbra:
+        pb["umbra"] = float(make_workload.umbra)
+        label += ", umbra=%g (scan)" % pb["umbra"]
+    if make_workload.spacing:
+        pb["spacing"] = float(make_workload.spacing)
+        label += ", spacing=%g (scan)" % pb["spacing"]
     if unconfined:
         pb["confined"] = False
         label += ", confined=False"
@@ -100,6 +106,9 @@ def make_workload(name, realizations, npaths, seed, unconfined=False):
                     spacing=float(pb["spacing"]), umbra=float(pb["umbra"]), confined=bool(pb["confined"]),
                     tol=float(pb["tol"]), maxstep=float(pb["maxstep"]))
     return spec, params, label
+
+
+make_workload.umbra = make_workload.spacing = None      # --umbra / --spacing: lattice scans (tools/ab_run.sh), never the default line
 
 
 def host_sampling_rate(pb, R):
@@ -487,12 +496,16 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
               "bitset_word_ops_per_s_estimate": segs_step / step_s * rows_seg * 1.25,
               "note": "cells registered = bits set in the per-realization bitmaps = sum of the count grid; word ops = one RED.OR per window row (x1.25 for rows straddling a word)"}
     if cx.red:
-        raster["roofline"] = {"bound": "atomic (bit-set RED.OR to L2)", "achieved": raster["bitset_word_ops_per_s_estimate"] / 1e9,
-                              "peak": cx.red["l2_lane_private"] * cx.world, "unit": "1e9 word ops/s (all GPUs)",
-                              "frac": raster["bitset_word_ops_per_s_estimate"] / 1e9 / (cx.red["l2_lane_private"] * cx.world),
+        peak = cx.red["l2_sector_per_lane"] * cx.world
+        raster["roofline"] = {"bound": "atomic (bit-set RED.OR to L2, one 32-byte sector per lane: every lane rasterises another particle)",
+                              "achieved": raster["bitset_word_ops_per_s_estimate"] / 1e9, "peak": peak, "unit": "1e9 word ops/s (all GPUs)",
+                              "frac": raster["bitset_word_ops_per_s_estimate"] / 1e9 / peak,
+                              "frac_of_coalesced_peak": raster["bitset_word_ops_per_s_estimate"] / 1e9 / (cx.red["l2_lane_private"] * cx.world),
                               "peaks": cx.red,
-                              "reading": "the rasteriser is far from its atomic roofline: it is bound by the instructions that find each row's interval, "
-                                         "not by the bit-set traffic (ncu: RED wavefronts 24 % of the L1 peak at C5)"}
+                              "reading": "peak = oneka_red_probe mode 4 (the rasteriser's own pattern: a sector per lane, a bitmap row further per operation); "
+                                         "the coalesced lane-private figure (8 lanes per sector) is not reachable by particles that are cells apart. "
+                                         "ncu at C5 (profiles/r02_track_kernel_c5_final_raw.csv): L2 tag throughput 64 %, L1-to-crossbar 56 %, issue slots 65 % -- "
+                                         "co-limited by the bit-set traffic and by the instructions that find each row's interval"}
 
     # ---- roofline of the fused tracking + raster kernel (this rank) ----
     if cx.probe_tf is None:
@@ -685,7 +698,7 @@ def run_ours(args):
     cx.max_mhz = sampler.max_mhz
     ff = "off" if args.farfield == "off" else "auto"
     try:                                           # the rasteriser's roofline denominators (rank-local, ~50 ms)
-        cx.red = {"l2_lane_private": eng.red_probe(0)[0], "l2_warp_contended": eng.red_probe(1)[0],
+        cx.red = {"l2_sector_per_lane": eng.red_probe(4)[0], "l2_lane_private": eng.red_probe(0)[0], "l2_warp_contended": eng.red_probe(1)[0],
                   "shared_lane_private": eng.red_probe(2)[0], "shared_warp_contended": eng.red_probe(3)[0],
                   "unit": "1e9 atomic word operations/s, oneka_red_probe"}
     except Exception as exc:
@@ -817,7 +830,12 @@ def main():
     ap.add_argument("--farfield", default="auto", choices=["auto", "off"],
                     help="auto: tiled far-field expansion of the well sum where it pays (default); off: direct sums only")
     ap.add_argument("--unconfined", action="store_true", help="confined=False: the head-dependent velocity of model.py:353-389")
+    ap.add_argument("--umbra", type=float, default=0.0, help="lattice scans only: override the workload's umbra (turns the extra legs off)")
+    ap.add_argument("--spacing", type=float, default=0.0, help="lattice scans only: override the workload's grid spacing (turns the extra legs off)")
     args = ap.parse_args()
+    make_workload.umbra, make_workload.spacing = args.umbra or None, args.spacing or None
+    if args.umbra or args.spacing:
+        args.legs = "none"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -93,6 +93,12 @@ oneka_ctx *oneka_create(int device);                    /* NULL on failure; see 
 void       oneka_destroy(oneka_ctx *ctx);
 int        oneka_set_stream(oneka_ctx *ctx, void *cuda_stream);         /* cudaStream_t; NULL = legacy default */
 int        oneka_set_workspace_limit(oneka_ctx *ctx, uint64_t bytes);   /* cap for the per-realization registration bitmaps */
+/* The rasteriser (ProbabilityField.insert, oneka/probabilityfield.py:296-310) has two flavours with identical results: the
+ * plain one, and one for lattices where a segment's window spans many rows (umbra >> deltay), which issues fewer bit-set
+ * operations (64-bit RED.OR; rows wholly behind the start of a segment, which the previous segment of the path already set,
+ * are not set again) for a few more instructions per row.  mode 0 (default): chosen from the lattice handed to each capture
+ * call (2 umbra / deltay + 1 >= 8 rows with direct well sums, >= 11 with the far field: heavy);  1: always plain;  2: always heavy. */
+int        oneka_set_raster_mode(oneka_ctx *ctx, int32_t mode);
 int        oneka_synchronize(oneka_ctx *ctx);
 uint64_t   oneka_launch_count(const oneka_ctx *ctx);    /* kernels launched by this context so far */
 /* When enabled, CUDA events bracket every launch of the tracking/raster kernel and of the flush
@@ -279,7 +285,9 @@ int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host
  * The rasteriser's memory operation is a bit-set: RED.OR of one 32-bit word per lattice row per segment
  * (insert(), oneka/probabilityfield.py:296-310 sets rgrid[i, j] node by node).  mode 0: RED.OR to L2, every lane its own
  * word of a `span_bytes` buffer (uncontended);  mode 1: the same with all 32 lanes of a warp on ONE word (contended);
- * mode 2: atomicOr on shared memory, every lane its own word;  mode 3: shared memory, one word per warp.
+ * mode 2: atomicOr on shared memory, every lane its own word;  mode 3: shared memory, one word per warp;
+ * mode 4: RED.OR to L2 with every lane on its OWN 32-byte sector, moving on by one bitmap row per operation -- the rasteriser's
+ * own access pattern (each lane tracks another particle; mode 0 packs 8 lanes into a sector and needs 8x fewer L2 requests).
  * gops_out = 1e9 atomic word-operations per second (best of 5).  Synchronous.                                    */
 int oneka_red_probe(oneka_ctx *ctx, int32_t mode, uint64_t span_bytes, int32_t iters, double *gops_out, double *ms_out);
 

@@ -53,6 +53,7 @@ struct oneka_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_per_sm = 0;                 // cudaDevAttrMaxSharedMemoryPerMultiprocessor
+    int raster_mode = 0;                    // 0: rasteriser flavour by lattice (raster_heavy), 1: plain, 2: heavy
     cudaStream_t stream = nullptr;
     unsigned int *bitmaps = nullptr;        // registration bitmaps, all-zero between calls
     size_t bitmap_bytes = 0;
@@ -104,7 +105,8 @@ struct oneka_ctx {
 // One CTA = THREADS consecutive paths of ONE realization; grid = R * ceil(P/THREADS).
 // FF: the realization's far-field coefficient table and the tiles' near lists are staged behind the well store (see
 // "Far-field compression" in oneka_device.cuh); ORD = its order when that is a compile-time constant, else 0.
-template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS>
+// HEAVY: the rasteriser's flavour for windows of many rows (raster_seg<true>), chosen per lattice by raster_heavy().
+template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS, bool HEAVY = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff)
 {
@@ -160,7 +162,7 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
         __syncthreads();
     }
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE, FF, ORD>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
+    dopri_track<CONFINED, MODE, FF, ORD, HEAVY>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
 }
 
 // c[r][tile][k] = sum_w w_rw P[tile][w][k]:  a (realizations x wells) . (wells x tiles*order) product with complex P, i.e. a
@@ -302,7 +304,8 @@ flush_kernel(unsigned int *bitmaps, long long nslots, long long slots_per_y, Lat
         if (cnt[b]) atomicAdd(row + b, cnt[b]);
 }
 
-// test hook: one thread per given trace, same raster_seg as the fused kernel
+// test hook: one thread per given trace, same raster_seg as the fused kernel (consecutive segments of a trace chain)
+template <bool HEAVY>
 __global__ void __launch_bounds__(128)
 raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, const double *verts,
                      const int *real_of, long long s0, long long s1, unsigned int *bitmaps, unsigned long long *stats)
@@ -317,8 +320,10 @@ raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, 
     unsigned int *bm = bitmaps + (size_t)(r - s0) * L.words;
     RasterCounters ctr = {0u, 0u};
     unsigned long long nseg = 0;
+    bool chained = false;
     for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
-        raster_seg(L, s_lat, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3], ctr);
+        chained |= raster_seg<HEAVY>(L, s_lat, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3],
+                                     ctr, chained);
         ++nseg;
     }
     atomicAdd(stats + STAT_STEPS, nseg);
@@ -375,13 +380,17 @@ distsq_kernel(long long n, const double *__restrict__ abc, double *__restrict__ 
 }
 
 // Atomic bit-set probes: the memory operation of the rasteriser (one RED.OR per lattice row per segment).
-//   SHARED false: RED.OR.b32 to global memory (resolved in L2), `words` words of target, lane-private or one word per warp
-//   SHARED true : ATOMS.OR on a 32 KB shared-memory tile
-template <bool SHARED, bool CONTENDED>
+//   MODE 0: RED.OR.b32 to global memory (resolved in L2), consecutive lanes on consecutive words (4 sectors per warp request)
+//   MODE 1: the same, all 32 lanes of a warp on one word
+//   MODE 2 / 3: ATOMS.OR on a 32 KB shared-memory tile, lane-private / one word per warp
+//   MODE 4: RED.OR.b32 to global memory, EVERY LANE ITS OWN 32-BYTE SECTOR, moving on by one bitmap row (160 words) per
+//           operation -- the rasteriser's own pattern (each lane is another particle; a segment's rows are 620 B apart at C5)
+template <int MODE>
 __global__ void __launch_bounds__(256)
 red_probe_kernel(unsigned int *buf, unsigned long long words, int iters, unsigned int *sink)
 {
     __shared__ unsigned int tile[8192];
+    constexpr bool SHARED = (MODE == 2 || MODE == 3), CONTENDED = (MODE == 1 || MODE == 3);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned long long gthread = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (SHARED) {
@@ -395,6 +404,16 @@ red_probe_kernel(unsigned int *buf, unsigned long long words, int iters, unsigne
         }
         __syncthreads();
         if (tile[threadIdx.x] == 0xdeadbeefu) sink[0] = 1u;  // never true; keeps the tile alive
+        return;
+    }
+    if (MODE == 4) {
+        unsigned long long idx = (gthread * 40503ull) % words;     // lanes far apart: one sector each
+#pragma unroll 4
+        for (int k = 0; k < iters; ++k) {
+            atomicOr(buf + idx, 1u << ((k + lane) & 31));
+            idx += 160ull;                                          // the next row of the window
+            if (idx >= words) idx -= words;
+        }
         return;
     }
     // global: consecutive lanes on consecutive words (the coalesced pattern of neighbouring bitmap words), each warp
@@ -496,7 +515,8 @@ static int make_lattice(const oneka_lattice *lat, LatticeDev &L)
     if (lat->nrows <= 0 || lat->ncols <= 0) return fail(ONEKA_ERR_ARG, "lattice must have nrows, ncols > 0");
     if (!(lat->umbra >= 0.0)) return fail(ONEKA_ERR_ARG, "umbra must be >= 0");
     L.xmin = lat->xmin; L.ymin = lat->ymin; L.dx = lat->deltax; L.dy = lat->deltay;
-    L.nrows = lat->nrows; L.ncols = lat->ncols; L.wpr = (lat->ncols + 31) / 32;
+    L.nrows = lat->nrows; L.ncols = lat->ncols;
+    L.wpr = ((lat->ncols + 63) / 64) * 2;                        // an even number of words: every bitmap row starts on 8 bytes (raster_seg<true>'s 64-bit bit-sets)
     L.umbra = lat->umbra;
     L.umbra2 = lat->umbra * lat->umbra;
     L.dx32 = (float)lat->deltax; L.dy32 = (float)lat->deltay; L.umbra2_32 = (float)L.umbra2;
@@ -583,12 +603,25 @@ static size_t ff_smem_unc(const FarFieldDev &ff)
 // system; the kernel's static shared memory is ~200 B)
 static size_t ff_smem_budget(const oneka_ctx *ctx, int min_ctas) { return ctx->smem_per_sm / (size_t)min_ctas - 1024 - 512; }
 
-template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS>
+// The rasteriser's flavour for this lattice: a segment's window spans about 2 umbra / deltay + 1 rows (+ its own rise).  From
+// a certain number of rows on, the bit-set traffic to L2 costs more than the heavy flavour's extra instructions -- earlier in the
+// direct-sum kernels (24 resident warps per SM keep more bit-sets in flight) than in the far-field kernels (16 warps, bound by
+// instruction latency).  Measured on B200, profiles/r02_flavour_scan.txt: direct kernel 7 rows 0 %, 9 rows -6 %, 11 rows -13 %;
+// far-field kernel 9 rows +1 %, 11 rows -1 %.  ctx->raster_mode 1 / 2 force plain / heavy (oneka_set_raster_mode).
+constexpr double RASTER_HEAVY_ROWS = 8.0, RASTER_HEAVY_ROWS_FF = 11.0;
+static bool raster_heavy(const oneka_ctx *ctx, const LatticeDev &L, bool farfield = false)
+{
+    if (ctx->raster_mode == 1) return false;
+    if (ctx->raster_mode == 2) return true;
+    return 2.0 * L.umbra / L.dy + 1.0 >= (farfield ? RASTER_HEAVY_ROWS_FF : RASTER_HEAVY_ROWS);
+}
+
+template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS, bool HEAVY>
 static int launch_one(oneka_ctx *ctx, const TrackParams &tp, const LatticeDev &L, unsigned int *bitmaps, const FarFieldDev &ff, size_t smem)
 {
     const long long nblk = tp.R * ((tp.P + THREADS - 1) / THREADS);
     if (nblk > 0x7fffffffLL) return fail(ONEKA_ERR_ARG, "too many CTAs in one launch (%lld)", nblk);
-    auto kern = track_kernel<CONFINED, MODE, FF, ORD, THREADS, MIN_CTAS>;
+    auto kern = track_kernel<CONFINED, MODE, FF, ORD, THREADS, MIN_CTAS, HEAVY>;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblk, THREADS, smem, ctx->stream>>>(tp, L, bitmaps, ff);
     return ONEKA_OK;
@@ -606,16 +639,21 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     FarFieldDev none;
     memset(&none, 0, sizeof(none));
     int rc;
+    constexpr bool H = (MODE == 1);                              // only the fused kernels rasterise: MODE 0 / 2 have one flavour
+    const bool heavy = H && raster_heavy(ctx, L, ff != nullptr);
+#define ONEKA_LAUNCH(C, F, O, T, M, FFV) (heavy ? launch_one<C, MODE, F, O, T, M, H>(ctx, tp, L, bitmaps, FFV, smem) \
+                                                : launch_one<C, MODE, F, O, T, M, false>(ctx, tp, L, bitmaps, FFV, smem))
     if (m->confined && ff && ff->order == FF_ORDER_UNROLLED)
-        rc = launch_one<true, MODE, true, FF_ORDER_UNROLLED, FF_THREADS, FF_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+        rc = ONEKA_LAUNCH(true, true, FF_ORDER_UNROLLED, FF_THREADS, FF_MIN_CTAS, *ff);
     else if (m->confined && ff)
-        rc = launch_one<true, MODE, true, 0, FF_THREADS, FF_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+        rc = ONEKA_LAUNCH(true, true, 0, FF_THREADS, FF_MIN_CTAS, *ff);
     else if (m->confined)
-        rc = launch_one<true, MODE, false, 0, TRACK_THREADS, TRACK_MIN_CTAS>(ctx, tp, L, bitmaps, none, smem);
+        rc = ONEKA_LAUNCH(true, false, 0, TRACK_THREADS, TRACK_MIN_CTAS, none);
     else if (ff)
-        rc = launch_one<false, MODE, true, 0, FF_UNC_THREADS, FF_UNC_MIN_CTAS>(ctx, tp, L, bitmaps, *ff, smem);
+        rc = ONEKA_LAUNCH(false, true, 0, FF_UNC_THREADS, FF_UNC_MIN_CTAS, *ff);
     else
-        rc = launch_one<false, MODE, false, 0, TRACK_THREADS, TRACK_MIN_CTAS>(ctx, tp, L, bitmaps, none, smem);
+        rc = ONEKA_LAUNCH(false, false, 0, TRACK_THREADS, TRACK_MIN_CTAS, none);
+#undef ONEKA_LAUNCH
     if (rc) return rc;
     prof_end(ctx);
     ctx->launches++;
@@ -836,6 +874,13 @@ int oneka_set_stream(oneka_ctx *ctx, void *cuda_stream)
     if (!ctx) return fail(ONEKA_ERR_ARG, "ctx is NULL");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->stream = (cudaStream_t)cuda_stream;
+    return ONEKA_OK;
+}
+
+int oneka_set_raster_mode(oneka_ctx *ctx, int32_t mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return fail(ONEKA_ERR_ARG, "oneka_set_raster_mode: mode must be 0 (by lattice), 1 (plain) or 2 (heavy)");
+    ctx->raster_mode = mode;
     return ONEKA_OK;
 }
 
@@ -1112,8 +1157,12 @@ int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntrace
     if (rc) return rc;
     for (long long s0 = 0; s0 < nreal; s0 += slots) {
         const long long s1 = (s0 + slots < nreal) ? s0 + slots : nreal;
-        raster_traces_kernel<<<(unsigned)((ntraces + 127) / 128), 128, 0, ctx->stream>>>(
-            L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
+        if (raster_heavy(ctx, L))
+            raster_traces_kernel<true><<<(unsigned)((ntraces + 127) / 128), 128, 0, ctx->stream>>>(
+                L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
+        else
+            raster_traces_kernel<false><<<(unsigned)((ntraces + 127) / 128), 128, 0, ctx->stream>>>(
+                L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         rc = launch_flush(ctx, L, s1 - s0, counts_dev);
@@ -1448,7 +1497,7 @@ int oneka_distancesquared_host(oneka_ctx *ctx, int64_t n, const double *abc_host
 
 int oneka_red_probe(oneka_ctx *ctx, int32_t mode, uint64_t span_bytes, int32_t iters, double *gops_out, double *ms_out)
 {
-    if (!ctx || mode < 0 || mode > 3 || iters <= 0) return fail(ONEKA_ERR_ARG, "bad argument to oneka_red_probe");
+    if (!ctx || mode < 0 || mode > 4 || iters <= 0) return fail(ONEKA_ERR_ARG, "bad argument to oneka_red_probe");
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (span_bytes < 4096) span_bytes = 4096;
     const unsigned long long words = span_bytes / 4;
@@ -1459,10 +1508,11 @@ int oneka_red_probe(oneka_ctx *ctx, int32_t mode, uint64_t span_bytes, int32_t i
     const int blocks = ctx->sm_count * 8, threads = 256;
     auto launch = [&](int it) {
         switch (mode) {
-        case 0: red_probe_kernel<false, false><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
-        case 1: red_probe_kernel<false, true><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
-        case 2: red_probe_kernel<true, false><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
-        default: red_probe_kernel<true, true><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 0: red_probe_kernel<0><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 1: red_probe_kernel<1><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 2: red_probe_kernel<2><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        case 3: red_probe_kernel<3><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
+        default: red_probe_kernel<4><<<blocks, threads, 0, ctx->stream>>>(buf, words, it, sink); break;
         }
     };
     cudaEvent_t a, b;

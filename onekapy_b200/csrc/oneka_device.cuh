@@ -617,8 +617,21 @@ __device__ __forceinline__ double floor_div(double v, double org, double delta, 
     return f;
 }
 
-__device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_lat, unsigned int *__restrict__ bm,
-                                           const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr)
+// HEAVY: the flavour for lattices where a segment meets many rows (umbra >> spacing; C5: 11-15 rows), where the kernel is
+// co-limited by the bit-set traffic to L2 (one 32-byte sector per lane per row: ncu at C5, L2 tag throughput 64 %).  It issues
+// fewer bit-sets, for a few more instructions per row (which is why windows of 5-7 rows, C3 / C4, keep the plain flavour:
+// measured, profiles/r02_notes.md section 10):
+//   * 64-bit RED.OR on the aligned word pair: a span straddles a pair half as often as a word (1.12 instead of 1.25 per row);
+//   * `chained`: the path's previous chronicled segment ended at (ax, ay) and went through this function with the same clip
+//     window.  Its cap b then set every node of the disc around a already, and the rows of THIS segment that lie wholly behind
+//     a (both interval ends on cap a: the row's nodes are exactly that disc's chord) have nothing to add: their bit-set is
+//     skipped.  Only rows on the fast path qualify -- both chord ends farther from a node than the FP32 bound, so the two
+//     segments' decisions for every node of the chord are the same exact decision.
+// Returns false when the segment had zero length (nothing marked, the chain is not established by it); true otherwise.
+template <bool HEAVY = false>
+__device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_lat, unsigned int *__restrict__ bm,
+                                           const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr,
+                                           bool chained = false)
 {
     // ---- window, probabilityfield.py:298-301 ----
     // left = floor((min(ax,bx) - umbra - xmin)/dx) etc.  Fast path: the four quotients in 16.16 fixed point from one
@@ -647,11 +660,11 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
     }
     const int left = max(fl, cw.l), right = min(fr + 1, cw.r), bottom = max(fb, cw.b), top = min(ft + 1, cw.t);
     if (fl < cw.l || fb < cw.b || fr + 1 > cw.r || ft + 1 > cw.t) ctr.clipped++;
-    if (left >= right || bottom >= top) return;                          // empty window
+    if (left >= right || bottom >= top) return true;                     // empty window (then the disc around b is outside the clip window too)
 
     const double bax = __dsub_rn(bx, ax), bay = __dsub_rn(by, ay);
     const double len2 = __dadd_rn(__dmul_rn(bax, bax), __dmul_rn(bay, bay));
-    if (!(len2 > 0.0)) return;                                           // 0/0 -> nan -> no node is marked
+    if (!(len2 > 0.0)) return false;                                     // 0/0 -> nan -> no node is marked
     const bool all_exact = len2 < 1e-20;
 
     // ---- FP32 set-up, relative to endpoint a ----
@@ -840,7 +853,16 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
         const int span = kr - kl;
         const bool fast = (dmin < scan_below) & (xr > xl) & (edge_ok | (cap_l & cap_r)) & !(amb_l | amb_r) & (span < 32);
         if (fast) {
-            if (span >= 0) {
+            if constexpr (HEAVY) {
+                if ((span >= 0) & !(chained & la & ra)) {
+                    const int ja = left + kl;
+                    unsigned long long *wp = reinterpret_cast<unsigned long long *>(row) + (ja >> 6);    // rows are 8-byte aligned (wpr is even)
+                    const int sh = ja & 63;
+                    const unsigned long long bits = (unsigned long long)(0xffffffffu >> (31 - span));
+                    atomicOr(wp, bits << sh);
+                    if (sh + span > 63) atomicOr(wp + 1, bits >> (64 - sh));
+                }
+            } else if (span >= 0) {
                 const int ja = left + kl;
                 unsigned int *wp = row + (ja >> 5);
                 const int sh = ja & 31;
@@ -852,6 +874,7 @@ __device__ __forceinline__ void raster_seg(const LatticeDev &L, const double *s_
             general_row(i, cay, row);
         }
     }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -866,7 +889,8 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
 //   FF: the far-field evaluation (confined: field_feval_ff<ORD>, ORD = compile-time order or 0; unconfined: field_feval_ff_unc)
-template <bool CONFINED, int MODE, bool FF = false, int ORD = 0>
+//   HEAVY: raster_seg's flavour for windows of many rows
+template <bool CONFINED, int MODE, bool FF = false, int ORD = 0, bool HEAVY = false>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
                                             long long r, int p, bool active,
@@ -907,6 +931,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
 
     double k1x = 0.0, k1y = 0.0;
     bool running = active;
+    bool chained = false;                                                  // raster_seg: an earlier segment of this path ended where the next one starts
     if (active) {
         x = tp.start_xy[2 * p];
         y = tp.start_xy[2 * p + 1];
@@ -993,7 +1018,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         }
         if (MODE == 1) {
             // chronicle the accepted step (capturezone.py:120 -> probabilityfield.py:338-339), then reconverge
-            if (seg) raster_seg(L, s_lat, bm, cw, sax, say, x, y, ctr);
+            if (seg) chained |= raster_seg<HEAVY>(L, s_lat, bm, cw, sax, say, x, y, ctr, chained);
             __syncwarp();
         }
     }

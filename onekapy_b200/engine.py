@@ -198,6 +198,14 @@ class Engine:
         self.use_stream(torch.cuda.current_stream(self.device))
         if workspace_limit is not None:
             _cabi.check(self._L.oneka_set_workspace_limit(self._h, int(workspace_limit)))
+        mode = os.environ.get("ONEKA_RASTER_MODE", "auto").lower()                    # A/B runs: plain | heavy
+        if mode != "auto":
+            self.set_raster_mode(mode)
+
+    def set_raster_mode(self, mode):
+        """Rasteriser flavour (oneka_set_raster_mode): "auto" = by lattice (heavy from 8 window rows on), "plain", "heavy".
+        Both set the same bits; they differ in how many bit-set operations reach L2."""
+        _cabi.check(self._L.oneka_set_raster_mode(self._h, {"auto": 0, "plain": 1, "heavy": 2}[str(mode).lower()]))
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -247,7 +255,8 @@ class Engine:
 
     def red_probe(self, mode, span_bytes=64 << 20, iters=4096):
         """Atomic bit-set throughput (1e9 word operations/s): mode 0 RED.OR to L2 lane-private words, 1 one word per warp,
-        2 shared-memory atomicOr lane-private, 3 shared memory one word per warp -- the rasteriser's roofline."""
+        2 shared-memory atomicOr lane-private, 3 shared memory one word per warp, 4 RED.OR to L2 with one 32-byte sector per
+        lane (the rasteriser's own pattern: its roofline)."""
         g, ms = C.c_double(0), C.c_double(0)
         _cabi.check(self._L.oneka_red_probe(self._h, int(mode), int(span_bytes), int(iters), C.byref(g), C.byref(ms)))
         return g.value, ms.value

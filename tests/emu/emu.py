@@ -42,6 +42,12 @@ def lib():
     return _lib
 
 
+def set_raster_heavy(heavy):
+    """Rasteriser flavour of the following calls: False = raster_seg<false>, True = raster_seg<true> (64-bit bit-sets, rows behind
+    the start of a chained segment skipped).  The library chooses by lattice (oneka_api.cu: raster_heavy); here the test does."""
+    lib().oneka_emu_set_raster_heavy(1 if heavy else 0)
+
+
 def _p(a):
     return None if a is None else a.ctypes.data
 

@@ -50,6 +50,7 @@ static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned int v) { return __builtin_ffs((int)v); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned int atomicOr(unsigned int *p, unsigned int v) { const unsigned int o = *p; *p = o | v; return o; }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o | v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = std::min(o, v); return o; }
 static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = std::max(o, v); return o; }
@@ -66,7 +67,7 @@ static void emu_lattice(double xmin, double ymin, double dx, double dy, int nrow
 {
     std::memset(&L, 0, sizeof(L));
     L.xmin = xmin; L.ymin = ymin; L.dx = dx; L.dy = dy;
-    L.nrows = nrows; L.ncols = ncols; L.wpr = (ncols + 31) / 32;
+    L.nrows = nrows; L.ncols = ncols; L.wpr = ((ncols + 63) / 64) * 2;      // make_lattice: an even number of words per row
     L.umbra = umbra;
     L.umbra2 = umbra * umbra;
     L.dx32 = (float)dx; L.dy32 = (float)dy; L.umbra2_32 = (float)L.umbra2;
@@ -81,6 +82,10 @@ static void emu_lattice(double xmin, double ymin, double dx, double dy, int nrow
 }
 
 extern "C" {
+
+// the rasteriser flavour of the next calls (oneka_set_raster_mode; launch_track's choice is by lattice): 0 plain, 1 heavy
+static int g_raster_heavy = 0;
+void oneka_emu_set_raster_heavy(int heavy) { g_raster_heavy = heavy ? 1 : 0; }
 
 // mode 0: tracking only; 1: track + rasterise + register (counts[nrows][ncols] +=); 2: vertices kept (verts[R][P][max_verts][2]).
 // far field: ff_order > 0 switches it on for the tile grid (ff_x0, ff_y0, ff_tile, ff_ntx, ff_nty), eta = ff_eta.
@@ -165,24 +170,24 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
             if (confined) {
                 if (use_ff && ff_order == 16) {                                                          // launch_track's choice: the unrolled order
                     if (mode == 0) dopri_track<true, 0, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                    else if (mode == 1) dopri_track<true, 1, true, 16>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
+                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, true, 16, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 16, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                     else dopri_track<true, 2, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 } else if (use_ff) {
                     if (mode == 0) dopri_track<true, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                    else if (mode == 1) dopri_track<true, 1, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
+                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, true, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                     else dopri_track<true, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 } else {
                     if (mode == 0) dopri_track<true, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                    else if (mode == 1) dopri_track<true, 1, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true);
+                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, false, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                     else dopri_track<true, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 }
             } else if (use_ff) {
                 if (mode == 0) dopri_track<false, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                else if (mode == 1) dopri_track<false, 1, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs);
+                else if (mode == 1) { if (g_raster_heavy) dopri_track<false, 1, true, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<false, 1, true, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                 else dopri_track<false, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
             } else {
                 if (mode == 0) dopri_track<false, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                else if (mode == 1) dopri_track<false, 1, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true);
+                else if (mode == 1) { if (g_raster_heavy) dopri_track<false, 1, false, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<false, 1, false, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                 else dopri_track<false, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
             }
         }
@@ -223,9 +228,15 @@ int oneka_emu_raster_traces(double xmin, double ymin, double dx, double dy, int 
         for (long long t = 0; t < ntraces; ++t) {
             if (real_of[t] != r) continue;
             RasterCounters ctr = {0u, 0u};
-            for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v)
-                raster_seg(L, s_lat, bitmap.data(), ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2],
-                           verts[2 * v + 3], ctr);
+            bool chained = false;                                  // raster_traces_kernel: consecutive segments of a trace chain
+            for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
+                if (g_raster_heavy)
+                    chained |= raster_seg<true>(L, s_lat, bitmap.data(), ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1],
+                                                verts[2 * v + 2], verts[2 * v + 3], ctr, chained);
+                else
+                    raster_seg<false>(L, s_lat, bitmap.data(), ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2],
+                                      verts[2 * v + 3], ctr);
+            }
             nexact += ctr.exact;
         }
         for (int i = 0; i < L.nrows; ++i)

@@ -50,8 +50,16 @@ def test_tracker_vs_executed_reference(golden, name):
     assert worst < 1e-9, worst
 
 
+@pytest.fixture(params=["plain", "heavy"])
+def flavour(request):
+    """Both rasteriser flavours (raster_seg<false> / raster_seg<true>) must set exactly the reference's bits."""
+    emu.set_raster_heavy(request.param == "heavy")
+    yield request.param
+    emu.set_raster_heavy(False)
+
+
 @pytest.mark.parametrize("name", CAPTURES)
-def test_fused_tracker_and_rasteriser_bit_exact(golden, name):
+def test_fused_tracker_and_rasteriser_bit_exact(golden, name, flavour):
     """dopri_track + raster_seg (MODE 1) + register: the executed reference's grid on the fixed lattice, cell for cell."""
     g = golden(name)
     s, spec, par = spec_of(g)
@@ -121,7 +129,7 @@ def test_far_field_200_wells_vs_direct():
     assert rel < 1e-12
 
 
-def test_rasteriser_insert_fixture_and_random_tracks(golden):
+def test_rasteriser_insert_fixture_and_random_tracks(golden, flavour):
     """raster_seg alone: hand-made tracks with exact ties (executed reference) and random tracks (oracle)."""
     from oracle import oracle as O
     g = golden("insert.npz")

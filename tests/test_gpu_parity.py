@@ -21,10 +21,13 @@ CAPTURES = ["det_basic.npz", "sto_basic.npz", "sto_perham.npz", "unc_basic.npz",
 POS_RTOL = 1e-6       # BASELINE.json north_star: endpoints within 1e-6 relative position
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["auto", "heavy", "plain"])
+def eng(request):
+    """Every test of this module runs three times: with the rasteriser flavour chosen by lattice (the default), and with each of
+    the two flavours forced (oneka_set_raster_mode) -- both must reproduce the reference's grids on every configuration."""
     from onekapy_b200.engine import Engine
     e = Engine(0)
+    e.set_raster_mode(request.param)
     yield e
     e.close()
 
@@ -567,7 +570,7 @@ def test_raster_traces_in_batches(eng, golden):
     gm = fixed_geom(g, s)
     tr = traces_of(g)
     real_of = np.repeat(np.arange(len(par)), s["P"]).astype(np.int32)
-    words = gm.nrows * ((gm.ncols + 31) // 32)
+    words = gm.nrows * 2 * ((gm.ncols + 63) // 64)                # bitmap rows hold an even number of 32-bit words
     small = Engine(0, workspace_limit=2 * words * 4)              # 2 slots for 6 realizations -> 3 batches
     n0 = small.launch_count()
     counts = small.raster_traces(gm, s["umbra"], tr, real_of, len(par))

@@ -114,7 +114,7 @@ def test_batching_independent_of_workspace(eng):
     geom, _ = lattice_for(eng, spec, dp)
     a = eng.new_counts(geom)
     eng.capture(spec, dp, geom, a)
-    words = geom.nrows * ((geom.ncols + 31) // 32)
+    words = geom.nrows * 2 * ((geom.ncols + 63) // 64)            # bitmap rows hold an even number of 32-bit words
     small = Engine(0, workspace_limit=7 * words * 4)           # 7 bitmaps -> 14 launches of the fused kernel
     dp2 = small.upload(spec, par)
     b = small.new_counts(geom)

@@ -150,8 +150,9 @@ def test_own_communicator_single_rank(eng):
 
 def test_atomic_probes(eng):
     """The rasteriser's roofline denominators: RED.OR to L2 (lane-private / one word per warp) and shared-memory atomicOr."""
-    res = {m: eng.red_probe(m, span_bytes=64 << 20, iters=512)[0] for m in range(4)}
-    print("atomic probes [1e9 word ops/s]: L2 lane-private %.1f, L2 warp-contended %.1f, shared lane-private %.1f, shared warp-contended %.1f"
-          % (res[0], res[1], res[2], res[3]))
+    res = {m: eng.red_probe(m, span_bytes=64 << 20, iters=512)[0] for m in range(5)}
+    print("atomic probes [1e9 word ops/s]: L2 lane-private %.1f, L2 warp-contended %.1f, shared lane-private %.1f, shared warp-contended %.1f, "
+          "L2 one sector per lane %.1f" % (res[0], res[1], res[2], res[3], res[4]))
     assert all(v > 1.0 for v in res.values())
     assert res[2] > res[0]                                        # shared memory beats L2
+    assert res[4] < res[0]                                        # a sector per lane costs more L2 requests than 8 lanes per sector
