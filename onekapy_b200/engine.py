@@ -203,9 +203,10 @@ class Engine:
             self.set_raster_mode(mode)
 
     def set_raster_mode(self, mode):
-        """Rasteriser flavour (oneka_set_raster_mode): "auto" = by lattice (heavy from 8 window rows on), "plain", "heavy".
-        Both set the same bits; they differ in how many bit-set operations reach L2."""
-        _cabi.check(self._L.oneka_set_raster_mode(self._h, {"auto": 0, "plain": 1, "heavy": 2}[str(mode).lower()]))
+        """Rasteriser flavour (oneka_set_raster_mode): "auto" = by lattice (plain for windows of few rows; from 8 rows on heavy, and
+        through the threads' shared-memory row tiles where the kernel has room for them), "plain", "heavy", "tile".
+        All set the same bits; they differ in how many bit-set operations reach L2."""
+        _cabi.check(self._L.oneka_set_raster_mode(self._h, {"auto": 0, "plain": 1, "heavy": 2, "tile": 3}[str(mode).lower()]))
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):

@@ -42,10 +42,11 @@ def lib():
     return _lib
 
 
-def set_raster_heavy(heavy):
-    """Rasteriser flavour of the following calls: False = raster_seg<false>, True = raster_seg<true> (64-bit bit-sets, rows behind
-    the start of a chained segment skipped).  The library chooses by lattice (oneka_api.cu: raster_heavy); here the test does."""
-    lib().oneka_emu_set_raster_heavy(1 if heavy else 0)
+def set_raster_flavour(name):
+    """Rasteriser flavour of the following calls: "plain" = raster_seg<RF_PLAIN>, "heavy" = RF_HEAVY (64-bit bit-sets, rows behind the
+    start of a chained segment skipped), "tile" = RF_TILE (heavy through the thread's row tile; direct-sum kernels only -- far-field
+    calls then run heavy, as in the library).  The library chooses by lattice (oneka_api.cu: raster_flavour); here the test does."""
+    lib().oneka_emu_set_raster_flavour({"plain": 0, "heavy": 1, "tile": 2}[name])
 
 
 def _p(a):

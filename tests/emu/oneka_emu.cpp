@@ -83,9 +83,13 @@ static void emu_lattice(double xmin, double ymin, double dx, double dy, int nrow
 
 extern "C" {
 
-// the rasteriser flavour of the next calls (oneka_set_raster_mode; launch_track's choice is by lattice): 0 plain, 1 heavy
-static int g_raster_heavy = 0;
-void oneka_emu_set_raster_heavy(int heavy) { g_raster_heavy = heavy ? 1 : 0; }
+// the rasteriser flavour of the next calls (oneka_set_raster_mode; launch_track's choice is by lattice): RF_PLAIN, RF_HEAVY, RF_TILE
+static int g_raster_flavour = 0;
+void oneka_emu_set_raster_flavour(int rf) { g_raster_flavour = (rf == 1 || rf == 2) ? rf : 0; }
+// the one emulated thread's row tile (track_kernel's static shared arrays, stride 1)
+static unsigned long long g_tile_bits[TILE_ROWS];
+static int g_tile_tag[TILE_ROWS];
+static const RasterTile g_tile = {g_tile_bits, g_tile_tag, 1};
 
 // mode 0: tracking only; 1: track + rasterise + register (counts[nrows][ncols] +=); 2: vertices kept (verts[R][P][max_verts][2]).
 // far field: ff_order > 0 switches it on for the tile grid (ff_x0, ff_y0, ff_tile, ff_ntx, ff_nty), eta = ff_eta.
@@ -170,24 +174,24 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
             if (confined) {
                 if (use_ff && ff_order == 16) {                                                          // launch_track's choice: the unrolled order
                     if (mode == 0) dopri_track<true, 0, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, true, 16, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 16, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
+                    else if (mode == 1) { if (g_raster_flavour) dopri_track<true, 1, true, 16, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 16, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                     else dopri_track<true, 2, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 } else if (use_ff) {
                     if (mode == 0) dopri_track<true, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, true, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
+                    else if (mode == 1) { if (g_raster_flavour) dopri_track<true, 1, true, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<true, 1, true, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                     else dopri_track<true, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 } else {
                     if (mode == 0) dopri_track<true, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                    else if (mode == 1) { if (g_raster_heavy) dopri_track<true, 1, false, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
+                    else if (mode == 1) { if (g_raster_flavour == 2) dopri_track<true, 1, false, 0, RF_TILE>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, FarFieldDev(), FarFieldShared(), g_tile); else if (g_raster_flavour) dopri_track<true, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                     else dopri_track<true, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 }
             } else if (use_ff) {
                 if (mode == 0) dopri_track<false, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
-                else if (mode == 1) { if (g_raster_heavy) dopri_track<false, 1, true, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<false, 1, true, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
+                else if (mode == 1) { if (g_raster_flavour) dopri_track<false, 1, true, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<false, 1, true, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
                 else dopri_track<false, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
             } else {
                 if (mode == 0) dopri_track<false, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                else if (mode == 1) { if (g_raster_heavy) dopri_track<false, 1, false, 0, true>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<false, 1, false, 0, false>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
+                else if (mode == 1) { if (g_raster_flavour == 2) dopri_track<false, 1, false, 0, RF_TILE>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, FarFieldDev(), FarFieldShared(), g_tile); else if (g_raster_flavour) dopri_track<false, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<false, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                 else dopri_track<false, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
             }
         }
@@ -229,14 +233,15 @@ int oneka_emu_raster_traces(double xmin, double ymin, double dx, double dy, int 
             if (real_of[t] != r) continue;
             RasterCounters ctr = {0u, 0u};
             bool chained = false;                                  // raster_traces_kernel: consecutive segments of a trace chain
+            const ClipWin all = {0, L.ncols, 0, L.nrows};
+            if (g_raster_flavour == RF_TILE) raster_tile_init(g_tile);
             for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
-                if (g_raster_heavy)
-                    chained |= raster_seg<true>(L, s_lat, bitmap.data(), ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1],
-                                                verts[2 * v + 2], verts[2 * v + 3], ctr, chained);
-                else
-                    raster_seg<false>(L, s_lat, bitmap.data(), ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2],
-                                      verts[2 * v + 3], ctr);
+                const double *a = verts + 2 * v;
+                if (g_raster_flavour == RF_TILE) chained |= raster_seg<RF_TILE>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr, chained, g_tile);
+                else if (g_raster_flavour == RF_HEAVY) chained |= raster_seg<RF_HEAVY>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr, chained);
+                else raster_seg<RF_PLAIN>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr);
             }
+            if (g_raster_flavour == RF_TILE) raster_tile_flush(g_tile, bitmap.data(), L.wpr);
             nexact += ctr.exact;
         }
         for (int i = 0; i < L.nrows; ++i)

@@ -50,12 +50,12 @@ def test_tracker_vs_executed_reference(golden, name):
     assert worst < 1e-9, worst
 
 
-@pytest.fixture(params=["plain", "heavy"])
+@pytest.fixture(params=["plain", "heavy", "tile"])
 def flavour(request):
-    """Both rasteriser flavours (raster_seg<false> / raster_seg<true>) must set exactly the reference's bits."""
-    emu.set_raster_heavy(request.param == "heavy")
+    """All rasteriser flavours (raster_seg<RF_PLAIN / RF_HEAVY / RF_TILE>) must set exactly the reference's bits."""
+    emu.set_raster_flavour(request.param)
     yield request.param
-    emu.set_raster_heavy(False)
+    emu.set_raster_flavour("plain")
 
 
 @pytest.mark.parametrize("name", CAPTURES)
