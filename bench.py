@@ -489,12 +489,18 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
     # reference; the kernel issues one RED.OR (two when the row's bits straddle a word) per row that meets the capsule
     mean_len = 0.9 * spec.maxstep                       # accepted steps sit at the space cap almost everywhere (controller, capturezone.py:247)
     rows_seg = (mean_len * 0.64 + 2 * spec.umbra) / spec.spacing + 1          # E|dy| = 2/pi x length for an isotropic direction
+    # bit-sets per window row: the plain flavour's spans straddle a 32-bit word in a quarter of the rows; the heavy flavour's
+    # 64-bit bit-sets straddle a pair in an eighth, and it skips the rows behind a chained segment's start (0.36 umbra / spacing
+    # of them for an isotropic direction).  Checked against ncu's RED counts at C5: 18.0 (plain) and 14.1 (heavy) per segment.
+    flavour = eng.raster_flavour(spec.umbra, spec.spacing, eng.farfield_info() is not None)
+    per_row = 1.25 if flavour == "plain" else 1.125 * (1.0 - 0.36 * (spec.umbra / spec.spacing) / rows_seg)
     raster = {"segments_per_s": segs_step / step_s, "cells_registered_per_s": cells_step / step_s,
               "cells_registered_per_segment": cells_step / max(1.0, segs_step),
               "exact_fp64_retests_per_segment": exact_step / max(1.0, segs_step),
               "window_rows_per_segment_estimate": rows_seg, "cell_tests_per_s_estimate": segs_step / step_s * rows_seg * rows_seg,
-              "bitset_word_ops_per_s_estimate": segs_step / step_s * rows_seg * 1.25,
-              "note": "cells registered = bits set in the per-realization bitmaps = sum of the count grid; word ops = one RED.OR per window row (x1.25 for rows straddling a word)"}
+              "bitset_word_ops_per_s_estimate": segs_step / step_s * rows_seg * per_row, "flavour": flavour, "bitsets_per_window_row": per_row,
+              "note": "cells registered = bits set in the per-realization bitmaps = sum of the count grid; word ops = one RED.OR per window row "
+                      "(plain flavour: x1.25 for rows straddling a word; heavy: 64-bit, x1.125, minus the skipped rows behind a chained segment's start)"}
     if cx.red:
         peak = cx.red["l2_sector_per_lane"] * cx.world
         raster["roofline"] = {"bound": "atomic (bit-set RED.OR to L2, one 32-byte sector per lane: every lane rasterises another particle)",
@@ -504,8 +510,8 @@ def run_leg(cx, name, wl, R, P, steps, warmup, seed, farfield="auto", unconfined
                               "peaks": cx.red,
                               "reading": "peak = oneka_red_probe mode 4 (the rasteriser's own pattern: a sector per lane, a bitmap row further per operation); "
                                          "the coalesced lane-private figure (8 lanes per sector) is not reachable by particles that are cells apart. "
-                                         "ncu at C5 (profiles/r02_track_kernel_c5_final_raw.csv): L2 tag throughput 64 %, L1-to-crossbar 56 %, issue slots 65 % -- "
-                                         "co-limited by the bit-set traffic and by the instructions that find each row's interval"}
+                                         "ncu at C5: plain flavour 151 G sector-REDs/s, L2 throughput 64 %, issue slots 65 %, long-scoreboard stalls on top "
+                                         "(atomic-bound); heavy flavour 22 % fewer bit-sets, issue slots 77 %, L2 57 % (profiles/r02_track_kernel_c5_*_raw.csv)"}
 
     # ---- roofline of the fused tracking + raster kernel (this rank) ----
     if cx.probe_tf is None:

@@ -99,6 +99,7 @@ int        oneka_set_workspace_limit(oneka_ctx *ctx, uint64_t bytes);   /* cap f
  * are not set again) for a few more instructions per row.  mode 0 (default): chosen from the lattice handed to each capture
  * call (2 umbra / deltay + 1 >= 8 rows with direct well sums, >= 11 with the far field: heavy);  1: always plain;  2: always heavy. */
 int        oneka_set_raster_mode(oneka_ctx *ctx, int32_t mode);
+int        oneka_raster_flavour(const oneka_ctx *ctx, double umbra, double deltay, int32_t farfield);   /* the flavour a capture on such a lattice runs: 0 plain, 1 heavy (< 0: error) */
 int        oneka_synchronize(oneka_ctx *ctx);
 uint64_t   oneka_launch_count(const oneka_ctx *ctx);    /* kernels launched by this context so far */
 /* When enabled, CUDA events bracket every launch of the tracking/raster kernel and of the flush

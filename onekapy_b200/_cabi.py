@@ -23,7 +23,7 @@ SYMBOLS = [
     "oneka_capture_clipped", "oneka_count_histogram", "oneka_gaussian_smooth", "oneka_capture_guarded",
     "oneka_set_farfield", "oneka_farfield_eval_host", "oneka_set_farfield_unconfined",
     "oneka_capture_tracked", "oneka_comm_unique_id", "oneka_comm_init_rank", "oneka_comm_attach", "oneka_comm_destroy",
-    "oneka_allreduce_counts", "oneka_allreduce_f64", "oneka_distancesquared_host", "oneka_red_probe", "oneka_farfield_info", "oneka_set_raster_mode",
+    "oneka_allreduce_counts", "oneka_allreduce_f64", "oneka_distancesquared_host", "oneka_red_probe", "oneka_farfield_info", "oneka_set_raster_mode", "oneka_raster_flavour",
 ]
 
 
@@ -119,6 +119,7 @@ def load():
     L.oneka_farfield_info.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.oneka_set_raster_mode.argtypes = [_vp, C.c_int32]
+    L.oneka_raster_flavour.argtypes = [_vp, C.c_double, C.c_double, C.c_int32]
     L.oneka_red_probe.argtypes = [_vp, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)                  # AttributeError here = header / library mismatch

@@ -53,7 +53,7 @@ struct oneka_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_per_sm = 0;                 // cudaDevAttrMaxSharedMemoryPerMultiprocessor
-    int raster_mode = 0;                    // 0: rasteriser flavour by lattice (raster_flavour), 1: plain, 2: heavy, 3: tile
+    int raster_mode = 0;                    // 0: rasteriser flavour by lattice (raster_flavour), 1: plain, 2: heavy
     cudaStream_t stream = nullptr;
     unsigned int *bitmaps = nullptr;        // registration bitmaps, all-zero between calls
     size_t bitmap_bytes = 0;
@@ -105,19 +105,14 @@ struct oneka_ctx {
 // One CTA = THREADS consecutive paths of ONE realization; grid = R * ceil(P/THREADS).
 // FF: the realization's far-field coefficient table and the tiles' near lists are staged behind the well store (see
 // "Far-field compression" in oneka_device.cuh); ORD = its order when that is a compile-time constant, else 0.
-// RF: the rasteriser's flavour (raster_seg<RF>), chosen per lattice by raster_flavour(); RF_TILE adds the threads' row tiles
-// (12 B x TILE_ROWS per thread of static shared memory: 24 KB for a 128-thread CTA; the far-field kernels have no room for it).
+// RF: the rasteriser's flavour (raster_seg<RF>), chosen per lattice by raster_flavour().
 template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS, int RF = RF_PLAIN>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff)
 {
-    static_assert(!(FF && RF == RF_TILE), "the far-field kernels' shared memory is taken by the coefficient tables");
     extern __shared__ double2 s_dyn[];
     __shared__ RealConsts rc;
     __shared__ double s_lat[5];
-    __shared__ unsigned long long s_tile_bits[RF == RF_TILE ? THREADS * TILE_ROWS : 1];
-    __shared__ int s_tile_tag[RF == RF_TILE ? THREADS * TILE_ROWS : 1];
-    const RasterTile tile = {s_tile_bits + (RF == RF_TILE ? threadIdx.x : 0), s_tile_tag + (RF == RF_TILE ? threadIdx.x : 0), THREADS};
     double *s_wells = reinterpret_cast<double *>(s_dyn);
     if (MODE == 1) stage_lattice(L, s_lat);
 
@@ -167,7 +162,7 @@ track_kernel(TrackParams tp, LatticeDev L, unsigned int *bitmaps, FarFieldDev ff
         __syncthreads();
     }
     unsigned int *bm = (MODE == 1) ? bitmaps + (size_t)r * L.words : nullptr;
-    dopri_track<CONFINED, MODE, FF, ORD, RF>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs, tile);
+    dopri_track<CONFINED, MODE, FF, ORD, RF>(tp, L, s_lat, bm, rc, s_wells, r, p, p < tp.P, ff, fs);
 }
 
 // c[r][tile][k] = sum_w w_rw P[tile][w][k]:  a (realizations x wells) . (wells x tiles*order) product with complex P, i.e. a
@@ -316,9 +311,6 @@ raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, 
                      const int *real_of, long long s0, long long s1, unsigned int *bitmaps, unsigned long long *stats)
 {
     __shared__ double s_lat[5];
-    __shared__ unsigned long long s_tile_bits[RF == RF_TILE ? 128 * TILE_ROWS : 1];
-    __shared__ int s_tile_tag[RF == RF_TILE ? 128 * TILE_ROWS : 1];
-    const RasterTile tile = {s_tile_bits + (RF == RF_TILE ? threadIdx.x : 0), s_tile_tag + (RF == RF_TILE ? threadIdx.x : 0), 128};
     stage_lattice(L, s_lat);
     __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -329,13 +321,12 @@ raster_traces_kernel(LatticeDev L, long long ntraces, const long long *offsets, 
     RasterCounters ctr = {0u, 0u};
     unsigned long long nseg = 0;
     bool chained = false;
-    if constexpr (RF == RF_TILE) raster_tile_init(tile);
     for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
         chained |= raster_seg<RF>(L, s_lat, bm, ClipWin{0, L.ncols, 0, L.nrows}, verts[2 * v], verts[2 * v + 1], verts[2 * v + 2], verts[2 * v + 3],
-                                  ctr, chained, tile);
+                                  ctr, chained);
         ++nseg;
     }
-    if constexpr (RF == RF_TILE) raster_tile_flush(tile, bm, L.wpr);
+
     atomicAdd(stats + STAT_STEPS, nseg);
     if (ctr.clipped) atomicAdd(stats + STAT_CLIPPED, (unsigned long long)ctr.clipped);
     if (ctr.exact) atomicAdd(stats + STAT_EXACT, (unsigned long long)ctr.exact);
@@ -616,22 +607,14 @@ static size_t ff_smem_budget(const oneka_ctx *ctx, int min_ctas) { return ctx->s
 // The rasteriser's flavour for this lattice: a segment's window spans about 2 umbra / deltay + 1 rows (+ its own rise).  From
 // a certain number of rows on, the bit-set traffic to L2 costs more than the heavy flavour's extra instructions -- earlier in the
 // direct-sum kernels (24 resident warps per SM keep more bit-sets in flight) than in the far-field kernels (16 warps, bound by
-// instruction latency).  Measured on B200, profiles/r02_flavour_scan.txt: direct kernel 7 rows 0 %, 9 rows -6 %, 11 rows -13 %;
-// far-field kernel 9 rows +1 %, 11 rows -1 %.  The direct-sum kernels, which have the shared memory for it, then also keep the
-// rows in the threads' tiles (RF_TILE) as long as a window fits the tile's TILE_ROWS slots and the tags hold the lattice
-// (row < 2^19, word pair < 2^12).  ctx->raster_mode 1 / 2 / 3 force plain / heavy / tile (oneka_set_raster_mode; tile falls
-// back to heavy where it cannot run).
+// instruction latency).  Measured on B200, profiles/r02_flavour_scan.txt: direct kernel 7 rows 0 %, 9 rows -6 %, 11 rows -13 %,
+// 15 rows -20 %; far-field kernel 9 rows +1 %, 11 rows -1 %.  ctx->raster_mode 1 / 2 force plain / heavy (oneka_set_raster_mode).
 constexpr double RASTER_HEAVY_ROWS = 8.0, RASTER_HEAVY_ROWS_FF = 11.0;
-static int raster_flavour(const oneka_ctx *ctx, const LatticeDev &L, bool farfield, double maxstep)
+static int raster_flavour(const oneka_ctx *ctx, const LatticeDev &L, bool farfield)
 {
-    const bool tile_ok = !farfield && L.nrows < (1 << 19) && L.wpr / 2 < (1 << 12);
     if (ctx->raster_mode == 1) return RF_PLAIN;
     if (ctx->raster_mode == 2) return RF_HEAVY;
-    if (ctx->raster_mode == 3) return tile_ok ? RF_TILE : RF_HEAVY;
-    const double rows = 2.0 * L.umbra / L.dy + 1.0;
-    if (rows < (farfield ? RASTER_HEAVY_ROWS_FF : RASTER_HEAVY_ROWS)) return RF_PLAIN;
-    const double window = rows + (maxstep > 0.0 ? maxstep / L.dy : 0.0) + 1.0;            // the tallest window of an accepted step
-    return (tile_ok && window <= (double)TILE_ROWS) ? RF_TILE : RF_HEAVY;
+    return (2.0 * L.umbra / L.dy + 1.0 >= (farfield ? RASTER_HEAVY_ROWS_FF : RASTER_HEAVY_ROWS)) ? RF_HEAVY : RF_PLAIN;
 }
 
 template <bool CONFINED, int MODE, bool FF, int ORD, int THREADS, int MIN_CTAS, int RF>
@@ -657,12 +640,11 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
     FarFieldDev none;
     memset(&none, 0, sizeof(none));
     int rc;
-    // only the fused kernels rasterise: MODE 0 / 2 have one flavour (the constants below collapse to RF_PLAIN for them)
-    constexpr int HV = (MODE == 1) ? RF_HEAVY : RF_PLAIN, TL = (MODE == 1) ? RF_TILE : RF_PLAIN;
-    const int rf = (MODE == 1) ? raster_flavour(ctx, L, ff != nullptr, tp.maxstep) : RF_PLAIN;
-#define ONEKA_LAUNCH(C, F, O, T, M, FFV) (rf == RF_TILE ? launch_one<C, MODE, F, O, T, M, (F ? HV : TL)>(ctx, tp, L, bitmaps, FFV, smem) \
-                                          : rf == RF_HEAVY ? launch_one<C, MODE, F, O, T, M, HV>(ctx, tp, L, bitmaps, FFV, smem) \
-                                                           : launch_one<C, MODE, F, O, T, M, RF_PLAIN>(ctx, tp, L, bitmaps, FFV, smem))
+    // only the fused kernels rasterise: MODE 0 / 2 have one flavour (HV collapses to RF_PLAIN for them)
+    constexpr int HV = (MODE == 1) ? RF_HEAVY : RF_PLAIN;
+    const int rf = (MODE == 1) ? raster_flavour(ctx, L, ff != nullptr) : RF_PLAIN;
+#define ONEKA_LAUNCH(C, F, O, T, M, FFV) (rf == RF_HEAVY ? launch_one<C, MODE, F, O, T, M, HV>(ctx, tp, L, bitmaps, FFV, smem) \
+                                                         : launch_one<C, MODE, F, O, T, M, RF_PLAIN>(ctx, tp, L, bitmaps, FFV, smem))
     if (m->confined && ff && ff->order == FF_ORDER_UNROLLED)
         rc = ONEKA_LAUNCH(true, true, FF_ORDER_UNROLLED, FF_THREADS, FF_MIN_CTAS, *ff);
     else if (m->confined && ff)
@@ -899,9 +881,18 @@ int oneka_set_stream(oneka_ctx *ctx, void *cuda_stream)
 
 int oneka_set_raster_mode(oneka_ctx *ctx, int32_t mode)
 {
-    if (!ctx || mode < 0 || mode > 3) return fail(ONEKA_ERR_ARG, "oneka_set_raster_mode: mode must be 0 (by lattice), 1 (plain), 2 (heavy) or 3 (tile)");
+    if (!ctx || mode < 0 || mode > 2) return fail(ONEKA_ERR_ARG, "oneka_set_raster_mode: mode must be 0 (by lattice), 1 (plain) or 2 (heavy)");
     ctx->raster_mode = mode;
     return ONEKA_OK;
+}
+
+int oneka_raster_flavour(const oneka_ctx *ctx, double umbra, double deltay, int32_t farfield)
+{
+    if (!ctx || !(deltay > 0.0) || !(umbra >= 0.0)) return fail(ONEKA_ERR_ARG, "bad argument to oneka_raster_flavour");
+    LatticeDev L;
+    memset(&L, 0, sizeof(L));
+    L.umbra = umbra; L.dy = deltay;
+    return raster_flavour(ctx, L, farfield != 0);
 }
 
 int oneka_set_workspace_limit(oneka_ctx *ctx, uint64_t bytes)
@@ -1178,10 +1169,7 @@ int oneka_raster_traces(oneka_ctx *ctx, const oneka_lattice *lat, int64_t ntrace
     for (long long s0 = 0; s0 < nreal; s0 += slots) {
         const long long s1 = (s0 + slots < nreal) ? s0 + slots : nreal;
         const unsigned nb = (unsigned)((ntraces + 127) / 128);
-        const int rf = raster_flavour(ctx, L, false, 0.0);      // (given traces have no step cap: the tile only when forced -- it is correct for any window)
-        if (rf == RF_TILE)
-            raster_traces_kernel<RF_TILE><<<nb, 128, 0, ctx->stream>>>(L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
-        else if (rf == RF_HEAVY)
+        if (raster_flavour(ctx, L, false) == RF_HEAVY)
             raster_traces_kernel<RF_HEAVY><<<nb, 128, 0, ctx->stream>>>(L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);
         else
             raster_traces_kernel<RF_PLAIN><<<nb, 128, 0, ctx->stream>>>(L, ntraces, (const long long *)offsets_dev, verts_dev, real_of_dev, s0, s1, ctx->bitmaps, ctx->stats_dev);

@@ -629,43 +629,15 @@ __device__ __forceinline__ double floor_div(double v, double org, double delta, 
 //     segments' decisions for every node of the chord are the same exact decision.
 // Returns false when the segment had zero length (nothing marked, the chain is not established by it); true otherwise.
 //
-// RF = RF_TILE: heavy, and the bit-sets go through the thread's ROW TILE in shared memory -- the tile that follows the
-// particle front.  Consecutive windows of a path overlap by ~80 % (C5: 12 rows, 2 new ones per step), so a row's word pair is
-// OR-ed in shared memory (plain LDS / STS: the tile is private to the thread) for as long as the particle's window covers it,
-// and reaches the global bitmap ONCE, when another row takes its slot (slot = row mod TILE_ROWS), when the span moves on to
-// another word pair, or at the end of the path (raster_tile_flush).  3-4 bit-sets per segment reach L2 instead of ~14.
-// Only for kernels with shared memory to spare (direct well sums: 12 B x TILE_ROWS per thread).
-constexpr int RF_PLAIN = 0, RF_HEAVY = 1, RF_TILE = 2;
-constexpr int TILE_ROWS = 16;
-struct RasterTile {                 // the thread's slots: bits[k * stride], tag[k * stride], k < TILE_ROWS;  tag = row << 12 | word pair, -1 = empty
-    unsigned long long *bits;
-    int *tag;
-    int stride;
-};
-
-__device__ __forceinline__ void raster_tile_init(const RasterTile &tile)
-{
-#pragma unroll
-    for (int k = 0; k < TILE_ROWS; ++k) { tile.tag[k * tile.stride] = -1; tile.bits[k * tile.stride] = 0ull; }
-}
-
-// every slot still held goes to the global bitmap (end of the path)
-__device__ __forceinline__ void raster_tile_flush(const RasterTile &tile, unsigned int *bm, int wpr)
-{
-#pragma unroll 4
-    for (int k = 0; k < TILE_ROWS; ++k) {
-        const int t = tile.tag[k * tile.stride];
-        if (t >= 0) {
-            atomicOr(reinterpret_cast<unsigned long long *>(bm + (size_t)(t >> 12) * wpr) + (t & 4095), tile.bits[k * tile.stride]);
-            tile.tag[k * tile.stride] = -1;
-        }
-    }
-}
-
+// (A third flavour kept each thread's rows in a shared-memory tile that followed the particle front -- OR-ed there, written to
+// the bitmap once when the window had moved on: 3-4 bit-sets per segment instead of ~14.  Bit-exact, and 9-13 % SLOWER than
+// RF_HEAVY on every lattice measured, profiles/r02_flavour_scan2.txt: once the bit-sets are down by a quarter the loop is bound
+// by its instructions, and the tile adds ~8 per row.  Commit e42da4e has it.)
+constexpr int RF_PLAIN = 0, RF_HEAVY = 1;
 template <int RF = RF_PLAIN>
 __device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_lat, unsigned int *__restrict__ bm,
                                            const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr,
-                                           bool chained = false, const RasterTile &tile = RasterTile())
+                                           bool chained = false)
 {
     constexpr bool HEAVY = RF != RF_PLAIN;
     // ---- window, probabilityfield.py:298-301 ----
@@ -888,25 +860,7 @@ __device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_
         const int span = kr - kl;
         const bool fast = (dmin < scan_below) & (xr > xl) & (edge_ok | (cap_l & cap_r)) & !(amb_l | amb_r) & (span < 32);
         if (fast) {
-            if constexpr (RF == RF_TILE) {
-                if ((span >= 0) & !(chained & la & ra)) {
-                    const int ja = left + kl;
-                    const int pair = ja >> 6, sh = ja & 63;
-                    const unsigned long long bits = (unsigned long long)(0xffffffffu >> (31 - span));
-                    const unsigned long long lo = bits << sh;
-                    const int k = (i & (TILE_ROWS - 1)) * tile.stride;
-                    const int mine = (i << 12) | pair;
-                    const int held = tile.tag[k];
-                    const unsigned long long old = tile.bits[k];
-                    const bool hit = held == mine;
-                    if (!hit & (held >= 0))                              // the slot's row leaves the tile: its bits go to the bitmap, once
-                        atomicOr(reinterpret_cast<unsigned long long *>(bm + (size_t)(held >> 12) * L.wpr) + (held & 4095), old);
-                    tile.bits[k] = hit ? (old | lo) : lo;
-                    tile.tag[k] = mine;
-                    if (sh + span > 63)                                  // the part in the next word pair: straight to the bitmap
-                        atomicOr(reinterpret_cast<unsigned long long *>(row) + pair + 1, bits >> (64 - sh));
-                }
-            } else if constexpr (HEAVY) {
+            if constexpr (HEAVY) {
                 if ((span >= 0) & !(chained & la & ra)) {
                     const int ja = left + kl;
                     unsigned long long *wp = reinterpret_cast<unsigned long long *>(row) + (ja >> 6);    // rows are 8-byte aligned (wpr is even)
@@ -942,13 +896,12 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
 //   FF: the far-field evaluation (confined: field_feval_ff<ORD>, ORD = compile-time order or 0; unconfined: field_feval_ff_unc)
-//   RF: raster_seg's flavour (RF_PLAIN, RF_HEAVY for windows of many rows, RF_TILE = heavy through the thread's shared-memory row tile)
+//   RF: raster_seg's flavour (RF_PLAIN, RF_HEAVY for windows of many rows)
 template <bool CONFINED, int MODE, bool FF = false, int ORD = 0, int RF = RF_PLAIN>
 __device__ __forceinline__ void dopri_track(const TrackParams &tp, const LatticeDev &L, const double *s_lat, unsigned int *bm,
                                             const RealConsts &rc, const double *s_wells,
                                             long long r, int p, bool active,
-                                            const FarFieldDev &ff = FarFieldDev(), const FarFieldShared &fs = FarFieldShared(),
-                                            const RasterTile &tile = RasterTile())
+                                            const FarFieldDev &ff = FarFieldDev(), const FarFieldShared &fs = FarFieldShared())
 {
     // the velocity: direct sum over the wells, or (FF, confined only) near wells + the tile's far-field polynomial
     auto feval = [&](double px, double py, double &ox, double &oy) -> int {
@@ -983,7 +936,6 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         cw.l = max(c.x, 0); cw.r = min(c.y, L.ncols); cw.b = max(c.z, 0); cw.t = min(c.w, L.nrows);
     }
 
-    if constexpr (MODE == 1 && RF == RF_TILE) raster_tile_init(tile);
     double k1x = 0.0, k1y = 0.0;
     bool running = active;
     bool chained = false;                                                  // raster_seg: an earlier segment of this path ended where the next one starts
@@ -1073,12 +1025,9 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         }
         if (MODE == 1) {
             // chronicle the accepted step (capturezone.py:120 -> probabilityfield.py:338-339), then reconverge
-            if (seg) chained |= raster_seg<RF>(L, s_lat, bm, cw, sax, say, x, y, ctr, chained, tile);
+            if (seg) chained |= raster_seg<RF>(L, s_lat, bm, cw, sax, say, x, y, ctr, chained);
             __syncwarp();
         }
-    }
-    if constexpr (MODE == 1 && RF == RF_TILE) {
-        if (active) raster_tile_flush(tile, bm, L.wpr);                    // what the tile still holds (the loop above ends warp-uniformly)
     }
 
     // ---- per-path outputs ----

@@ -203,10 +203,16 @@ class Engine:
             self.set_raster_mode(mode)
 
     def set_raster_mode(self, mode):
-        """Rasteriser flavour (oneka_set_raster_mode): "auto" = by lattice (plain for windows of few rows; from 8 rows on heavy, and
-        through the threads' shared-memory row tiles where the kernel has room for them), "plain", "heavy", "tile".
-        All set the same bits; they differ in how many bit-set operations reach L2."""
-        _cabi.check(self._L.oneka_set_raster_mode(self._h, {"auto": 0, "plain": 1, "heavy": 2, "tile": 3}[str(mode).lower()]))
+        """Rasteriser flavour (oneka_set_raster_mode): "auto" = by lattice (heavy from 8 window rows on with direct well sums, from
+        11 with the far field), "plain", "heavy".  Both set the same bits; they differ in how many bit-set operations reach L2."""
+        _cabi.check(self._L.oneka_set_raster_mode(self._h, {"auto": 0, "plain": 1, "heavy": 2}[str(mode).lower()]))
+
+    def raster_flavour(self, umbra, deltay, farfield):
+        """The flavour a capture on such a lattice runs (oneka_raster_flavour): "plain" or "heavy"."""
+        rf = self._L.oneka_raster_flavour(self._h, float(umbra), float(deltay), 1 if farfield else 0)
+        if rf < 0:
+            _cabi.check(rf)
+        return ("plain", "heavy")[rf]
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):

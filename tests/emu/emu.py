@@ -44,9 +44,8 @@ def lib():
 
 def set_raster_flavour(name):
     """Rasteriser flavour of the following calls: "plain" = raster_seg<RF_PLAIN>, "heavy" = RF_HEAVY (64-bit bit-sets, rows behind the
-    start of a chained segment skipped), "tile" = RF_TILE (heavy through the thread's row tile; direct-sum kernels only -- far-field
-    calls then run heavy, as in the library).  The library chooses by lattice (oneka_api.cu: raster_flavour); here the test does."""
-    lib().oneka_emu_set_raster_flavour({"plain": 0, "heavy": 1, "tile": 2}[name])
+    start of a chained segment skipped).  The library chooses by lattice (oneka_api.cu: raster_flavour); here the test does."""
+    lib().oneka_emu_set_raster_flavour({"plain": 0, "heavy": 1}[name])
 
 
 def _p(a):

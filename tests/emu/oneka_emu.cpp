@@ -83,13 +83,9 @@ static void emu_lattice(double xmin, double ymin, double dx, double dy, int nrow
 
 extern "C" {
 
-// the rasteriser flavour of the next calls (oneka_set_raster_mode; launch_track's choice is by lattice): RF_PLAIN, RF_HEAVY, RF_TILE
+// the rasteriser flavour of the next calls (oneka_set_raster_mode; launch_track's choice is by lattice): RF_PLAIN, RF_HEAVY
 static int g_raster_flavour = 0;
-void oneka_emu_set_raster_flavour(int rf) { g_raster_flavour = (rf == 1 || rf == 2) ? rf : 0; }
-// the one emulated thread's row tile (track_kernel's static shared arrays, stride 1)
-static unsigned long long g_tile_bits[TILE_ROWS];
-static int g_tile_tag[TILE_ROWS];
-static const RasterTile g_tile = {g_tile_bits, g_tile_tag, 1};
+void oneka_emu_set_raster_flavour(int rf) { g_raster_flavour = (rf == 1) ? 1 : 0; }
 
 // mode 0: tracking only; 1: track + rasterise + register (counts[nrows][ncols] +=); 2: vertices kept (verts[R][P][max_verts][2]).
 // far field: ff_order > 0 switches it on for the tile grid (ff_x0, ff_y0, ff_tile, ff_ntx, ff_nty), eta = ff_eta.
@@ -182,7 +178,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
                     else dopri_track<true, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 } else {
                     if (mode == 0) dopri_track<true, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                    else if (mode == 1) { if (g_raster_flavour == 2) dopri_track<true, 1, false, 0, RF_TILE>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, FarFieldDev(), FarFieldShared(), g_tile); else if (g_raster_flavour) dopri_track<true, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
+                    else if (mode == 1) { if (g_raster_flavour) dopri_track<true, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                     else dopri_track<true, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 }
             } else if (use_ff) {
@@ -191,7 +187,7 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
                 else dopri_track<false, 2, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
             } else {
                 if (mode == 0) dopri_track<false, 0, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
-                else if (mode == 1) { if (g_raster_flavour == 2) dopri_track<false, 1, false, 0, RF_TILE>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, FarFieldDev(), FarFieldShared(), g_tile); else if (g_raster_flavour) dopri_track<false, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<false, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
+                else if (mode == 1) { if (g_raster_flavour) dopri_track<false, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<false, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                 else dopri_track<false, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
             }
         }
@@ -234,14 +230,12 @@ int oneka_emu_raster_traces(double xmin, double ymin, double dx, double dy, int 
             RasterCounters ctr = {0u, 0u};
             bool chained = false;                                  // raster_traces_kernel: consecutive segments of a trace chain
             const ClipWin all = {0, L.ncols, 0, L.nrows};
-            if (g_raster_flavour == RF_TILE) raster_tile_init(g_tile);
             for (long long v = offsets[t]; v + 1 < offsets[t + 1]; ++v) {
                 const double *a = verts + 2 * v;
-                if (g_raster_flavour == RF_TILE) chained |= raster_seg<RF_TILE>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr, chained, g_tile);
-                else if (g_raster_flavour == RF_HEAVY) chained |= raster_seg<RF_HEAVY>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr, chained);
+                if (g_raster_flavour == RF_HEAVY) chained |= raster_seg<RF_HEAVY>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr, chained);
                 else raster_seg<RF_PLAIN>(L, s_lat, bitmap.data(), all, a[0], a[1], a[2], a[3], ctr);
             }
-            if (g_raster_flavour == RF_TILE) raster_tile_flush(g_tile, bitmap.data(), L.wpr);
+
             nexact += ctr.exact;
         }
         for (int i = 0; i < L.nrows; ++i)
