@@ -651,6 +651,8 @@ static int launch_track(oneka_ctx *ctx, const oneka_model_desc *m, const TrackPa
         rc = ONEKA_LAUNCH(true, true, 0, FF_THREADS, FF_MIN_CTAS, *ff);
     else if (m->confined)
         rc = ONEKA_LAUNCH(true, false, 0, TRACK_THREADS, TRACK_MIN_CTAS, none);
+    else if (ff && ff->order == FF_ORDER_UNROLLED)                 // (unrolled here too: C3 unconfined 94.8 -> 84.5 ms, profiles/r02_ab_unc16.txt)
+        rc = ONEKA_LAUNCH(false, true, FF_ORDER_UNROLLED, FF_UNC_THREADS, FF_UNC_MIN_CTAS, *ff);
     else if (ff)
         rc = ONEKA_LAUNCH(false, true, 0, FF_UNC_THREADS, FF_UNC_MIN_CTAS, *ff);
     else

@@ -478,6 +478,7 @@ __device__ __noinline__ FieldValue field_direct_unc_cold(const RealConsts &rc, c
     return v;
 }
 
+template <int ORD>
 __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const double *__restrict__ s_wells, int nw,
                                                   const FarFieldDev &ff, const FarFieldShared &fs,
                                                   double x, double y, double &fx, double &fy)
@@ -504,21 +505,27 @@ __device__ __forceinline__ int field_feval_ff_unc(const RealConsts &rc, const do
                   reinterpret_cast<const float *>(s_wells + (w >> 2) * WELL_BLK + 12)[w & 3], gx, gy, lsum32);
     }
     // far wells: discharge polynomial in FP64 ...
-    const int order = ff.order;
+    const int order = ORD > 0 ? ORD : ff.order;
     double re, im;
-    ff_poly_eval<0>(fs.c64 + tile * order, order, zr, zi, re, im);
+    ff_poly_eval<ORD>(fs.c64 + tile * order, order, zr, zi, re, im);
     gx += re;
     gy -= im;
     // ... and their potential in FP32:  Re(zeta T),  T = sum_j p_(j+1) zeta^j
     const float2 *pp = fs.p32 + tile * order;
     const float fr = (float)zr, fi = (float)zi;
     float ar = 0.0f, ai = 0.0f;
-#pragma unroll 2
-    for (int j = order - 1; j >= 0; --j) {
+    auto step32 = [&](int j) {
         const float2 c = pp[j];
         const float nr = fmaf(ar, fr, fmaf(-ai, fi, c.x));
         const float ni = fmaf(ar, fi, fmaf(ai, fr, c.y));
         ar = nr; ai = ni;
+    };
+    if constexpr (ORD > 0) {
+#pragma unroll
+        for (int j = ORD - 1; j >= 0; --j) step32(j);
+    } else {
+#pragma unroll 2
+        for (int j = order - 1; j >= 0; --j) step32(j);
     }
     const double pot_far = fs.b0[tile] + (double)fmaf(fr, ar, -(fi * ai));
     const double pot_reg = rc.A * dx0 * dx0 + rc.B * dy0 * dy0 + rc.c * dx0 * dy0 + rc.d * dx0 + rc.e * dy0 + rc.F;
@@ -634,6 +641,21 @@ __device__ __forceinline__ double floor_div(double v, double org, double delta, 
 // RF_HEAVY on every lattice measured, profiles/r02_flavour_scan2.txt: once the bit-sets are down by a quarter the loop is bound
 // by its instructions, and the tile adds ~8 per row.  Commit e42da4e has it.)
 constexpr int RF_PLAIN = 0, RF_HEAVY = 1;
+
+// bit-set of one 32-bit bitmap word on the rare rows (general_row).  The heavy flavour's common rows use 64-bit atomics on the
+// aligned word pairs, so its rare rows do too: every atomic a kernel issues on the bitmap then has one size (mixed-size
+// atomics on overlapping bytes are outside the PTX memory model's guarantees, whatever the L2 does with them today).
+template <bool WIDE>
+__device__ __forceinline__ void or_word(unsigned int *p, unsigned int mask)
+{
+    if constexpr (WIDE) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        atomicOr(reinterpret_cast<unsigned long long *>(a & ~(uintptr_t)7), (unsigned long long)mask << ((a & 4) ? 32 : 0));
+    } else {
+        atomicOr(p, mask);
+    }
+}
+
 template <int RF = RF_PLAIN>
 __device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_lat, unsigned int *__restrict__ bm,
                                            const ClipWin cw, double ax, double ay, double bx, double by, RasterCounters &ctr,
@@ -777,14 +799,14 @@ __device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_
                     const int sh = ja & 31;
                     if (span < 32) {
                         const unsigned int bits = 0xffffffffu >> (31 - span);
-                        atomicOr(wp, bits << sh);
-                        if (sh + span > 31) atomicOr(wp + 1, bits >> (32 - sh));
+                        or_word<HEAVY>(wp, bits << sh);
+                        if (sh + span > 31) or_word<HEAVY>(wp + 1, bits >> (32 - sh));
                     } else {
                         const int jb = left + kr;
 #pragma unroll 1
                         for (int w = ja >> 5; w <= (jb >> 5); ++w) {
                             const int lo = max(ja, w << 5), hi = min(jb, (w << 5) + 31);
-                            atomicOr(row + w, (0xffffffffu >> (31 - (hi - lo))) << (lo & 31));
+                            or_word<HEAVY>(row + w, (0xffffffffu >> (31 - (hi - lo))) << (lo & 31));
                         }
                     }
                 }
@@ -819,8 +841,8 @@ __device__ __forceinline__ bool raster_seg(const LatticeDev &L, const double *s_
             if (mask) {
                 const int sh = jc & 31;
                 unsigned int *wp = row + (jc >> 5);
-                atomicOr(wp, mask << sh);
-                if (sh && (mask >> (32 - sh))) atomicOr(wp + 1, mask >> (32 - sh));
+                or_word<HEAVY>(wp, mask << sh);
+                if (sh && (mask >> (32 - sh))) or_word<HEAVY>(wp + 1, mask >> (32 - sh));
             }
         }
     };
@@ -906,7 +928,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
     // the velocity: direct sum over the wells, or (FF, confined only) near wells + the tile's far-field polynomial
     auto feval = [&](double px, double py, double &ox, double &oy) -> int {
         if constexpr (FF && CONFINED) return field_feval_ff<ORD>(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
-        else if constexpr (FF) return field_feval_ff_unc(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
+        else if constexpr (FF) return field_feval_ff_unc<ORD>(rc, s_wells, tp.nw, ff, fs, px, py, ox, oy);
         else return field_feval<CONFINED>(rc, s_wells, tp.nw, px, py, ox, oy);
     };
     // Dormand-Prince tableau, capturezone.py:202-209

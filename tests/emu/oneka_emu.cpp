@@ -181,6 +181,10 @@ int oneka_emu_capture(int mode, int nw, const double *well_xy, double xo, double
                     else if (mode == 1) { if (g_raster_flavour) dopri_track<true, 1, false, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); else dopri_track<true, 1, false, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true); }
                     else dopri_track<true, 2, false>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true);
                 }
+            } else if (use_ff && ff_order == 16) {                                                   // launch_track's choice: the unrolled order
+                if (mode == 0) dopri_track<false, 0, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
+                else if (mode == 1) { if (g_raster_flavour) dopri_track<false, 1, true, 16, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<false, 1, true, 16, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
+                else dopri_track<false, 2, true, 16>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
             } else if (use_ff) {
                 if (mode == 0) dopri_track<false, 0, true>(tp, L, s_lat, nullptr, rc, s_wells.data(), r, p, true, ff, fs);
                 else if (mode == 1) { if (g_raster_flavour) dopri_track<false, 1, true, 0, RF_HEAVY>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); else dopri_track<false, 1, true, 0, RF_PLAIN>(tp, L, s_lat, bitmap.data(), rc, s_wells.data(), r, p, true, ff, fs); }
