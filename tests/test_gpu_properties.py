@@ -176,6 +176,35 @@ def test_c5_fine_grid_long_duration(eng):
     assert h.max() <= 32 and st["n_not_ok"] == 0
     check_subset(eng, spec, par, np.array([7]), geom)
     print("C5: lattice %dx%d (%.1f M nodes), steps %.3g, exact re-tests %d" % (geom.nrows, geom.ncols, geom.nrows * geom.ncols / 1e6, st["steps"], st["exact_tests"]))
+    # the two rasteriser flavours set the same bits (this lattice runs the heavy one by default: 11 window rows)
+    assert eng.raster_flavour(spec.umbra, spec.spacing, False) == "heavy"
+    try:
+        eng.set_raster_mode("plain")
+        plain = eng.new_counts(geom)
+        eng.capture(spec, dp, geom, plain)
+    finally:
+        eng.set_raster_mode("auto")
+    assert bool((plain == counts).all())
+
+
+@pytest.mark.parametrize("name,R,unconfined", [("c3", 256, False), ("c4", 64, False), ("c3", 64, True)])
+def test_raster_flavours_agree_on_far_field_kernels(eng, name, R, unconfined):
+    """Plain and heavy flavour of the far-field kernels (confined, unrolled order; 200 wells; unconfined): identical count grids."""
+    import bench
+    spec, par = bench.make_workload(name, R, 1000, 5, unconfined=unconfined)[:2]
+    dp = eng.upload(spec, par)
+    geom, st0 = lattice_for(eng, spec, dp)
+    grids = {}
+    try:
+        for mode in ("plain", "heavy"):
+            eng.set_raster_mode(mode)
+            grids[mode] = eng.new_counts(geom)
+            eng.reset_stats()
+            eng.capture(spec, dp, geom, grids[mode])
+            assert eng.read_stats()["n_not_ok"] == 0
+    finally:
+        eng.set_raster_mode("auto")
+    assert int(grids["plain"].sum().item()) > 0 and bool((grids["plain"] == grids["heavy"]).all())
 
 
 # ---- large well fields / many contexts -------------------------------------------------------------------------

@@ -156,3 +156,23 @@ def test_atomic_probes(eng):
     assert all(v > 1.0 for v in res.values())
     assert res[2] > res[0]                                        # shared memory beats L2
     assert res[4] < res[0]                                        # a sector per lane costs more L2 requests than 8 lanes per sector
+
+
+def test_raster_flavour_choice_and_modes(eng):
+    """oneka_raster_flavour / oneka_set_raster_mode: heavy from 8 window rows on with direct well sums, from 11 with the far field;
+    forcing a flavour overrides the lattice; a bad mode is refused."""
+    from onekapy_b200 import _cabi
+    assert eng.raster_flavour(8.0, 4.0, False) == "plain" and eng.raster_flavour(8.0, 4.0, True) == "plain"      # C3 / C4: 5 rows
+    assert eng.raster_flavour(14.0, 4.0, False) == "heavy" and eng.raster_flavour(14.0, 4.0, True) == "plain"    # 8 rows
+    assert eng.raster_flavour(20.0, 4.0, False) == "heavy" and eng.raster_flavour(20.0, 4.0, True) == "heavy"    # C5: 11 rows
+    try:
+        eng.set_raster_mode("heavy")
+        assert eng.raster_flavour(8.0, 4.0, True) == "heavy"
+        eng.set_raster_mode("plain")
+        assert eng.raster_flavour(20.0, 4.0, False) == "plain"
+    finally:
+        eng.set_raster_mode("auto")
+    with pytest.raises(_cabi.OnekaError):
+        _cabi.check(eng._L.oneka_set_raster_mode(eng._h, 7))
+    with pytest.raises(_cabi.OnekaError):
+        eng.raster_flavour(8.0, 0.0, False)
