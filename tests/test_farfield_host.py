@@ -206,3 +206,23 @@ def test_engine_far_field_policy_without_a_gpu():
     e3.farfield = "off"
     e3._auto_farfield(spec, geom)
     assert e3._L.calls == []
+
+
+def test_tile_lookup_edges():
+    """ff_locate's index arithmetic (rounding through 1.5 * 2^52, range check on the words of the sum): exact grid corners, points a
+    hair outside, points 2^32 and 2^40 tiles away (whose low word alone would look like a valid tile), inf and nan."""
+    wxy, w, xo, yo = _field("perham")
+    grid = farfield_grid((xo - 1400.0, xo + 1400.0, yo - 1400.0, yo + 1400.0), 380)
+    x0, y0, t, ntx, nty = grid["x0"], grid["y0"], grid["tile"], grid["ntx"], grid["nty"]
+    x1, y1 = x0 + ntx * t, y0 + nty * t
+    inside = np.array([[x0, y0], [x0 + 0.5 * t, y0], [x0, y0 + 2.0 * t], [x0 + 3.0 * t, y0 + 4.0 * t], [np.nextafter(x1, x0), np.nextafter(y1, y0)],
+                       [x0 + (ntx - 0.25) * t, y0 + (nty - 0.25) * t]])
+    outside = np.array([[x0 - 1e-6 * t, y0 + t], [x0 + t, y0 - 1e-6 * t], [x1 + 1e-6 * t, y0 + t], [x0 + t, y1 + 1e-6 * t],
+                        [x0 + (2.0 ** 32 + 3.5) * t, y0 + t], [x0 + t, y0 + (2.0 ** 40 + 1.5) * t], [x0 - (2.0 ** 32 - 3.5) * t, y0 + t],
+                        [np.inf, y0 + t], [x0 + t, -np.inf], [np.nan, y0 + t], [1e300, 1e300]])
+    out, near = _eval(wxy, w, xo, yo, grid, 16, 0.15, np.concatenate([inside, outside]))
+    assert np.all(near[:len(inside)] >= 0), near[:len(inside)]
+    assert np.all(near[len(inside):] == -1), near[len(inside):]
+    gx, gy, mag = _direct_ld(wxy, w, inside)
+    err = np.maximum(np.abs(out[:len(inside), 0] - gx), np.abs(out[:len(inside), 1] - gy)).astype(np.float64) / mag
+    assert err.max() < 1e-13, err
