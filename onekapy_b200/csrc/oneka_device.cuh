@@ -931,6 +931,13 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 }
 
 // ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__constant__ double c_dp[26] = {1.0 / 5.0, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,
+                                19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,
+                                9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,
+                                35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,
+                                71.0 / 57600.0, -1.0 / 40.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0};
+#endif
 // Dormand-Prince 5(4), capturezone.py:199-247.  One particle per thread.
 //   MODE 0: track only          MODE 1: track + rasterise          MODE 2: track + store vertices
 //   FF: the far-field evaluation (confined: field_feval_ff<ORD>, ORD = compile-time order or 0; unconfined: field_feval_ff_unc)
@@ -948,6 +955,17 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
         else return field_feval<CONFINED>(rc, s_wells, tp.nw, px, py, ox, oy);
     };
     // Dormand-Prince tableau, capturezone.py:202-209
+#ifdef __CUDA_ARCH__
+    // the tableau from the constant bank (LDCU.64 / .128 into uniform registers) instead of pairs of UMOV immediates: a third of the
+    // kernel's UMOVs gone, C3 -0.5 %, C5 -1.8 % (profiles/r02_ab_dpconst.txt)
+    const double a20 = c_dp[0];
+    const double a30 = c_dp[1], a31 = c_dp[2];
+    const double a40 = c_dp[3], a41 = c_dp[4], a42 = c_dp[5];
+    const double a50 = c_dp[6], a51 = c_dp[7], a52 = c_dp[8], a53 = c_dp[9];
+    const double a60 = c_dp[10], a61 = c_dp[11], a62 = c_dp[12], a63 = c_dp[13], a64 = c_dp[14];
+    const double a70 = c_dp[15], a72 = c_dp[16], a73 = c_dp[17], a74 = c_dp[18], a75 = c_dp[19];
+    const double e0 = c_dp[20], e1 = c_dp[21], e2 = c_dp[22], e3 = c_dp[23], e4 = c_dp[24], e5 = c_dp[25];
+#else
     constexpr double a20 = 1.0 / 5.0;
     constexpr double a30 = 3.0 / 40.0, a31 = 9.0 / 40.0;
     constexpr double a40 = 44.0 / 45.0, a41 = -56.0 / 15.0, a42 = 32.0 / 9.0;
@@ -955,6 +973,7 @@ __device__ __forceinline__ void dopri_track(const TrackParams &tp, const Lattice
     constexpr double a60 = 9017.0 / 3168.0, a61 = -355.0 / 33.0, a62 = 46732.0 / 5247.0, a63 = 49.0 / 176.0, a64 = -5103.0 / 18656.0;
     constexpr double a70 = 35.0 / 384.0, a72 = 500.0 / 1113.0, a73 = 125.0 / 192.0, a74 = -2187.0 / 6784.0, a75 = 11.0 / 84.0;
     constexpr double e0 = 71.0 / 57600.0, e1 = -1.0 / 40.0, e2 = -71.0 / 16695.0, e3 = 71.0 / 1920.0, e4 = -17253.0 / 339200.0, e5 = 22.0 / 525.0;
+#endif
     constexpr double EPS = DBL_EPSILON;                                   // :200
 
     const double duration = tp.duration, tol = tp.tol, maxstep = tp.maxstep;
