@@ -642,6 +642,12 @@ def dropin_leg(cx, R, P, steps):
                                              pb["wells"], obs, pb["spacing"], pb["umbra"], pb["confined"], pb["tol"], pb["maxstep"],
                                              rng=np.random.default_rng(1), engine=eng)
     np.random.seed(12345)
+    # the objects this process has piled up by now (problem tables, parity traces, JSON pieces) go to the permanent generation: a full
+    # collection that rescans them in the middle of a 146 ms call showed up as one 150-210 ms call among five (tools/dropin_calls.py
+    # in a fresh process: 145.5-147 ms every call, collector on or off)
+    import gc
+    gc.collect()
+    gc.freeze()
     for _ in range(2):
         call()
     cx.torch.cuda.synchronize(cx.dev)
@@ -654,6 +660,7 @@ def dropin_leg(cx, R, P, steps):
         each.append(round(1e3 * (time.perf_counter() - tc), 2))
         att += eng.last_stats["attempts"]
     secs = time.perf_counter() - t0
+    gc.unfreeze()
     # where a call's time goes: the three pieces of create_stochastic_capturezone timed one by one on the same problem
     from onekapy_b200.host.stochastic import sample_realizations
     from onekapy_b200.host.probabilityfield import ProbabilityField
@@ -672,7 +679,7 @@ def dropin_leg(cx, R, P, steps):
     t3 = time.perf_counter()
     ProbabilityField.from_counts(res["geom"], res["counts"], res["total_weight"])
     fld_s = time.perf_counter() - t3
-    return {"value": att / secs, "unit": "DOPRI5 attempts/s", "realizations_per_s": R * steps / secs, "ms_per_call": 1e3 * secs / steps, "ms_each_call": each, "steps": steps,
+    return {"value": att / secs, "unit": "DOPRI5 attempts/s", "realizations_per_s": R * steps / secs, "ms_per_call": 1e3 * secs / steps, "ms_each_call": each, "ms_per_call_median": float(np.median(each)), "steps": steps,
             "host_sampling_ms_per_call": 1e3 * host_s, "engine_run_exact_ms_per_call": 1e3 * eng_s, "probabilityfield_from_counts_ms": 1e3 * fld_s,
             "grid": [int(pf.nrows), int(pf.ncols)], "total_weight": float(pf.total_weight),
             "affected_realizations": eng.last_stats.get("affected_realizations"),
