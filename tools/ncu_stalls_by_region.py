@@ -11,7 +11,7 @@ src = open(os.path.join(here, "..", "onekapy_b200", "csrc", "oneka_device.cuh"))
 def find(s):
     return next(i + 1 for i, l in enumerate(src) if s in l)
 b = {k: find(v) for k, v in dict(poly="void ff_poly_eval", loc="bool ff_locate", ff="int field_feval_ff(", unc="// ---- unconfined flow through the far field",
-                                 raster="void raster_seg", dkey="unsigned long long dkey", dopri="void dopri_track", stage="void stage_realization",
+                                 raster="bool raster_seg(", dkey="unsigned long long dkey", dopri="void dopri_track", stage="void stage_realization",
                                  feval="int field_feval(").items()}
 reg = {"scaled_term + rcp": (30, b["feval"] - 1), "direct well loops": (b["feval"], b["poly"] - 40), "horner": (b["poly"], b["loc"] - 1), "tile lookup": (b["loc"], b["ff"] - 10),
        "regional + near wells": (b["ff"] - 9, b["unc"] - 1), "unconfined far field": (b["unc"], b["raster"] - 60), "rasteriser": (b["raster"] - 59, b["dkey"] - 1),
